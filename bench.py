@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the TracerAdvectionDiffusion hot path (BASELINE.json metric: grid-point RK4 steps/sec, fp64).
+
+Workload at N GPUs: BASELINE.json configs[1] — examples/cellularflow.jl scaled to 4096^2 (kappa = 0.1, RK4,
+steady cellular flow, fp64) — one independent tracer problem per GPU (ensemble sharding, no data-path
+collective => "scaling": "weak").
+
+One bench "step" = one frame of the example's loop, ``stepforward!(prob, nsubs=25)`` (examples/cellularflow.jl:134):
+  * ``value``  : grid-point RK4 steps/s with everything resident in HBM (device-timed, CUDA events, max over ranks)
+  * ``e2e``    : the same frame through the C ABI with HOST buffers: ``set_c!`` from pinned host memory (H2D),
+                 ``stepforward!(prob, 25)``, ``updatevars!`` into pinned host memory (D2H), all inside the timed region
+  * ``roofline``: dominant kernel, algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
+  * ``cpu_baseline``: the CPU oracle port (NumPy + threaded pocketfft) on a bounded sample of the same workload
+
+``--impl reference`` times the CPU restatement of the reference path (the reference itself is Julia + FFTW, neither
+of which exists in this image — see DESIGN.md) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NSUBS = 25          # RK4 steps per frame (examples/cellularflow.jl:33)
+METRIC = "grid-point RK4 steps/sec (fp64)"
+UNIT = "grid-point-steps/s"
+
+
+def workload(nx):
+    """examples/cellularflow.jl:30-81 scaled to nx^2 with an RK4-stable dt."""
+    Lx = 2 * np.pi
+    kappa = 0.1
+    dt = 0.5 * 2.785 / (kappa * 2 * (nx / 2) ** 2)
+    x = -Lx / 2 + (Lx / nx) * np.arange(nx)
+    X, Y = x[None, :], x[:, None]
+    psi0 = 0.2
+    u = np.ascontiguousarray(np.broadcast_to(psi0 * np.cos(X) * np.sin(Y), (nx, nx)))
+    v = np.ascontiguousarray(np.broadcast_to(-psi0 * np.sin(X) * np.cos(Y), (nx, nx)))
+    c0 = np.ascontiguousarray(0.5 * np.exp(-((X - 0.2 * Lx) ** 2 + Y ** 2) / (2 * 0.15 ** 2)))
+    return dict(nx=nx, Lx=Lx, kappa=kappa, dt=dt, u=u, v=v, c0=c0)
+
+
+def b_alg(ndim, stepper="RK4"):
+    """Algorithmic bytes per grid point per step (SURVEY section 8d / BASELINE.md section 3)."""
+    b = 128 * ndim + 176
+    if stepper.startswith("Filtered"):
+        b += 4
+    if stepper.endswith("ETDRK4"):
+        b -= 16
+    return b
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons during the timed region (NVML; nvidia-smi fallback)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_port_rate(w, seconds_budget=20.0, min_steps=2, max_steps=8):
+    """Time the CPU oracle (port of the reference path) on a bounded sample: a few RK4 steps of the same workload."""
+    from oracle.ptf_oracle import OracleProblem
+    cores = os.cpu_count() or 1
+    nx = w["nx"]
+    o = OracleProblem(n=(nx, nx), L=(w["Lx"], w["Lx"]), kappa=(w["kappa"], w["kappa"]), dt=w["dt"], stepper="RK4",
+                      velocity=[w["u"], w["v"]], steady=True, workers=cores)
+    o.set_c(w["c0"])
+    o.stepforward(1)   # warm-up (thread pool, page faults)
+    n = 0
+    t0 = time.perf_counter()
+    while n < max_steps and (n < min_steps or time.perf_counter() - t0 < seconds_budget):
+        o.stepforward(1)
+        n += 1
+    dtm = time.perf_counter() - t0
+    import scipy
+    return {"value": nx * nx * n / dtm, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} RK4 steps of the {nx}x{nx} cellular-flow workload, NumPy {np.__version__} elementwise + "
+                      f"scipy.fft {scipy.__version__} (pocketfft) workers={cores}; NOT Julia/FFTW (absent from the image)",
+            "ms_per_rk4_step": 1e3 * dtm / n}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    w = workload(args.nx)
+    # each "step" of the reference arm is a bounded sample: one RK4 step of the workload (a frame is 25 of them)
+    from oracle.ptf_oracle import OracleProblem
+    cores = os.cpu_count() or 1
+    nx = w["nx"]
+    o = OracleProblem(n=(nx, nx), L=(w["Lx"], w["Lx"]), kappa=(w["kappa"], w["kappa"]), dt=w["dt"], stepper="RK4",
+                      velocity=[w["u"], w["v"]], steady=True, workers=cores)
+    o.set_c(w["c0"])
+    for _ in range(args.warmup):
+        o.stepforward(1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.stepforward(1)
+    dtm = time.perf_counter() - t0
+    val = nx * nx * args.steps / dtm
+    import scipy
+    sample = (f"each step = 1 RK4 step (1/{NSUBS} of a frame) of the {nx}x{nx} cellular-flow workload; CPU restatement of "
+              f"the reference path (NumPy {np.__version__} + scipy.fft {scipy.__version__} pocketfft, workers={cores}); "
+              "the reference's Julia/FFTW runtime is absent from this image")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dtm / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cellularflow_{nx}x{nx}_RK4_kappa0.1 (BASELINE configs[1])", "nx": nx, "ny": nx,
+                       "stepper": "RK4", "dt": w["dt"]},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=4096)
+    ap.add_argument("--engine", default="auto", choices=["auto", "cufft", "fused"])
+    ap.add_argument("--stepper", default="RK4")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        args.steps = 4 if args.steps is None else args.steps
+        args.warmup = 1 if args.warmup is None else args.warmup
+        run_reference(args, rank, world)
+        return
+    args.steps = 8 if args.steps is None else args.steps
+    args.warmup = 3 if args.warmup is None else max(3, args.warmup)
+
+    import ctypes as C
+
+    import torch   # plumbing only: pinned host memory + torch.distributed barrier / max-reduce
+    import ptf_b200 as P
+    capi = P._capi
+    lib = capi.load()
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    w = workload(args.nx)
+    nx = w["nx"]
+    npts = nx * nx
+    flow = P.TwoDAdvectingFlow(u=lambda x, y: 0.2 * np.cos(x) * np.sin(y), v=lambda x, y: -0.2 * np.sin(x) * np.cos(y),
+                               steadyflow=True)
+    prob = P.Problem(P.B200(device=local_rank, engine=args.engine), flow, nx=nx, Lx=w["Lx"], kappa=w["kappa"],
+                     dt=w["dt"], stepper=args.stepper)
+    h = prob._h
+    # pinned host buffers for the e2e leg
+    c_in = torch.from_numpy(w["c0"].copy()).pin_memory()
+    c_out = torch.empty_like(c_in).pin_memory()
+    p_in = C.cast(c_in.data_ptr(), C.POINTER(C.c_double))
+    p_out = C.cast(c_out.data_ptr(), C.POINTER(C.c_double))
+    capi.check(lib.ptf_set_c(h, p_in, 0), h)
+
+    # ---------------- device-resident leg (value) ----------------
+    for _ in range(args.warmup):
+        prob.stepforward(NSUBS)
+    own0, libc0 = prob.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dev_ms += prob.step_timed(NSUBS)      # CUDA events on the step stream, per frame
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    sampler.stop_flag.set()
+    sampler.join()
+    own1, libc1 = prob.launch_count()
+    dev_ms = max_over_ranks(dev_ms)
+    wall_ms = max_over_ranks(wall_ms)
+    value = world * npts * NSUBS * args.steps / (dev_ms * 1e-3)
+
+    # sanity: the state must still be finite (a NaN run is not a measurement)
+    capi.check(lib.ptf_get_c(h, p_out), h)
+    finite = bool(torch.isfinite(c_out).all().item())
+
+    # ---------------- e2e leg: host buffers through the C ABI ----------------
+    for _ in range(2):
+        capi.check(lib.ptf_set_c(h, p_in, 0), h)
+        capi.check(lib.ptf_step(h, NSUBS), h)
+        capi.check(lib.ptf_get_c(h, p_out), h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        capi.check(lib.ptf_set_c(h, p_in, 0), h)       # H2D from pinned memory + r2c
+        capi.check(lib.ptf_step(h, NSUBS), h)          # stepforward!(prob, 25)
+        capi.check(lib.ptf_get_c(h, p_out), h)         # updatevars! + D2H into pinned memory
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": world * npts * NSUBS * args.steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": npts * 8, "d2h_bytes_per_step": npts * 8,
+           "ms_per_step": 1e3 * e2e_s / args.steps,
+           "call": "ptf_set_c(pinned host) + ptf_step(25) + ptf_get_c(pinned host)"}
+
+    # ---------------- roofline of the dominant kernel (live CUDA-event timing, in place) ----------------
+    peak, peak_src = peaks()
+    engine = prob.engine
+    roof = None
+    kernels = {}
+    if engine == "fused":
+        cands = [("ykernel", None), ("xkernel", None)]
+    else:
+        cands = [("deriv", 3 * 16 * (nx // 2 + 1) * nx), ("z2d", 2 * 8 * npts), ("d2z", 2 * 8 * npts)]
+    for name, alg_bytes in cands:
+        try:
+            ms = prob.kernel_time_ms(name, 20)
+        except Exception as e:   # a kernel name this engine does not have
+            continue
+        kernels[name] = {"ms": ms, "alg_bytes": alg_bytes}
+    step_bytes = b_alg(2, args.stepper) * npts
+    step_ms = dev_ms / (args.steps * NSUBS)
+    if engine == "fused" and kernels:
+        pass  # filled by the fused-engine branch below once it reports its own algorithmic bytes
+    if kernels:
+        top = max(kernels.items(), key=lambda kv: kv[1]["ms"])
+        name, k = top
+        if k["alg_bytes"]:
+            ach = k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src, "ms_per_launch": k["ms"]}
+    step_roof = {"b_alg_bytes_per_point_step": b_alg(2, args.stepper), "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
+                 "peak": peak, "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                 "ms_per_rk4_step": step_ms}
+    if roof is None:
+        roof = {"bound": "hbm", "kernel": "whole RK4 step", "achieved": step_roof["achieved"], "peak": peak,
+                "unit": "GB/s", "frac": step_roof["frac"], "traffic": None, "peak_source": peak_src}
+
+    # ---------------- CPU baseline (rank 0, N == 1) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_port_rate(w)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"cellularflow_{nx}x{nx}_{args.stepper}_kappa0.1 (BASELINE configs[1]), one "
+                                       f"independent problem per GPU", "nx": nx, "ny": nx, "stepper": args.stepper,
+                           "dt": w["dt"], "rk4_steps_per_step": NSUBS, "engine": engine,
+                           "l2": "inputs larger than L2 (each field 134 MB > 126 MB L2); no explicit flush",
+                           "state_finite": finite, "wall_ms_per_step": wall_ms / args.steps},
+                "e2e": e2e, "gpu_launches": own1 - own0, "library_calls": libc1 - libc0,
+                "roofline": roof, "step_roofline": step_roof, "kernels": kernels, "cpu_baseline": cpu,
+                "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

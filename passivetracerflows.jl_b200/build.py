@@ -1,0 +1,73 @@
+"""Build libptf_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels to the GPU box)."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libptf_b200.so")
+SOURCES = ["ptf_api.cu", "engine_cufft.cu", "engine_fused.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _newest(paths):
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "ptf_b200.h"),
+                                                                 os.path.abspath(__file__)]
+    return _newest(deps) > os.path.getmtime(LIB)
+
+
+def build(force=False, verbose=False, with_nccl=True):
+    if not force and not needs_build():
+        return LIB
+    nvcc = _nvcc()
+    objs = []
+    common = [nvcc, "-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
+              "-I", os.path.join(HERE, "..", "include")]
+    if verbose:
+        common += ["-Xptxas", "-v"]
+    if with_nccl:
+        common += ["-DPTF_WITH_NCCL"]
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        objs.append(o)
+        src = os.path.join(CSRC, s)
+        if (not force) and os.path.exists(o) and os.path.getmtime(o) > _newest(
+                [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [src]):
+            continue
+        procs.append((s, subprocess.Popen(common + ["-c", src, "-o", o], stdout=subprocess.PIPE,
+                                          stderr=subprocess.STDOUT, text=True)))
+    for s, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(out)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {s}")
+    link = [nvcc, "-shared", *ARCH, "-o", LIB, *objs, "-L/usr/local/cuda/lib64", "-lcufft",
+            "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+    if with_nccl:
+        link += ["-lnccl"]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
