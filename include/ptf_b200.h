@@ -176,6 +176,10 @@ int32_t ptf_device_bytes(const ptf_handle* h, int64_t* bytes);
 /* device-side diagnostics (callers' side of the path: FF Diagnostic-style scalars without a full read-back) */
 int32_t ptf_diag(ptf_handle* h, double* mean_c, double* variance_c, double* max_abs_sol);
 
+/* test hook: `count` independent length-n (power of two, 256..4096) complex transforms through the hand-written
+ * shared-memory FFT core; dir = -1 forward, +1 unnormalised inverse; interleaved complex128 host buffers */
+int32_t ptf_selftest_fft(int32_t n, int32_t dir, int32_t count, const double* in_host, double* out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,7 @@ SIGNATURES = {
     "ptf_kernel_timed": (C.c_int32, [_H, C.c_char_p, C.c_int32, C.POINTER(C.c_float)]),
     "ptf_device_bytes": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
     "ptf_diag": (C.c_int32, [_H, _DP, _DP, _DP]),
+    "ptf_selftest_fft": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _DP, _DP]),
 }
 
 _lib = None

@@ -10,29 +10,11 @@
 #include <cstring>
 
 #include "ptf_pointwise.cuh"
+#include "ptf_velocity.cuh"
 
 namespace ptf {
 
 namespace {
-
-constexpr int MAX_TERMS = 8;
-
-struct SepFlow {      // u_comp(x,y,z,t) = sum_m a[m] * X[m][i] * Y[m][j] * Z[m][k]
-  int nterms = 0;
-  const double* xt = nullptr;  // [nterms][nx]
-  const double* yt = nullptr;  // [nterms][ny]
-  const double* zt = nullptr;  // [nterms][nz]
-  const double* a = nullptr;   // [nterms] device-resident coefficients a_m(t_n): refreshed per step without
-                               // touching the captured graph
-};
-
-struct VelArgs {
-  int kind = 0;                                    // PTF_FLOW_*
-  const double* arr[3] = {nullptr, nullptr, nullptr};  // array form (STEADY / CALLBACK / LAYERED)
-  int64_t member_stride = 0;                       // 0 when one field is shared by all members
-  const double* ushift = nullptr;                  // LAYERED: U(y, layer) added to u, may be null
-  SepFlow sep[3];
-};
 
 struct SpecShape {
   int64_t nkr, ny, nz, B;
@@ -83,18 +65,6 @@ __global__ void __launch_bounds__(256) k_replicate(double* __restrict__ c, int64
     double v = c[i];
     for (int64_t b = 1; b < B; ++b) c[b * npts + i] = v;
   }
-}
-
-__device__ __forceinline__ double sep_eval(const SepFlow& f, int64_t i, int64_t j, int64_t k, int64_t nx, int64_t ny,
-                                           int64_t nz, int nd) {
-  double u = 0.0;
-  for (int m = 0; m < f.nterms; ++m) {
-    double t = f.a[m] * f.xt[m * nx + i];
-    if (nd >= 2) t *= f.yt[m * ny + j];
-    if (nd >= 3) t *= f.zt[m * nz + k];
-    u += t;
-  }
-  return u;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -158,17 +128,8 @@ __global__ void __launch_bounds__(256) k_product(double* __restrict__ g0, const 
 // ---------------------------------------------------------------------------------------------------
 // stage combine (FF timesteppers.jl), one pass; see CombineMode.
 // ---------------------------------------------------------------------------------------------------
-struct CombinePtrs {
-  const double2* Nh;  // transformed nonlinear term of this stage
-  double2* s0;        // sol
-  double2* s1;        // stage state / sol_1
-  double2* s2;        // ETDRK4 sol_2
-  double2* acc;       // RK4 accumulator / ETD N2+N3 / LSRK S2 / AB3 RHS_{-1}
-  double2* n1;        // ETD N1 / AB3 RHS_{-2}
-  const double *E, *E2, *zeta, *alpha, *beta, *gamma;  // ETDRK4 coefficient arrays [nz][ny][nkr]
-};
-
-__global__ void __launch_bounds__(256) k_combine(CombinePtrs P, CombineArgs A, AxisTables ax, SpecShape sh) {
+__global__ void __launch_bounds__(256) k_combine(const double2* __restrict__ Nh, CombinePtrs P, CombineArgs A,
+                                                  AxisTables ax, SpecShape sh) {
   int64_t row = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
   int64_t nrows = sh.ny * sh.nz * sh.B;
   if (row >= nrows) return;
@@ -177,157 +138,8 @@ __global__ void __launch_bounds__(256) k_combine(CombinePtrs P, CombineArgs A, A
   int64_t crow = (iz * sh.ny + iy) * sh.nkr;  // row base in the (batch-shared) coefficient arrays
   double ky = ax.ky[iy], kz = ax.kz[iz];
   int64_t base = row * sh.nkr;
-  const double dt = A.dt;
-  for (int64_t ix = threadIdx.x; ix < sh.nkr; ix += blockDim.x) {
-    int64_t i = base + ix;
-    double kx = ax.kx[ix];
-    double2 Nh = P.Nh[i];
-    double f = 1.0;
-    switch (A.mode) {
-      case CM_RK4_S1: {
-        double L = lin_op(ax, kx, ky, kz);
-        double2 s0 = P.s0[i];
-        double2 k = cadd(Nh, cmul_r(s0, L));
-        P.acc[i] = cdiv_r(k, 6.0);
-        P.s1[i] = cadd(s0, cmul_r(k, dt / 2));
-      } break;
-      case CM_RK4_S2:
-      case CM_RK4_S3: {
-        double L = lin_op(ax, kx, ky, kz);
-        double2 ss = P.s1[i];
-        double2 k = cadd(Nh, cmul_r(ss, L));
-        P.acc[i] = cadd(P.acc[i], cdiv_r(k, 3.0));
-        double h = (A.mode == CM_RK4_S2) ? dt / 2 : dt;
-        P.s1[i] = cadd(P.s0[i], cmul_r(k, h));
-      } break;
-      case CM_RK4_S4: {
-        double L = lin_op(ax, kx, ky, kz);
-        double2 ss = P.s1[i];
-        double2 k = cadd(Nh, cmul_r(ss, L));
-        double2 sum = cadd(P.acc[i], cdiv_r(k, 6.0));
-        double2 r = cadd(P.s0[i], cmul_r(sum, dt));
-        if (A.filtered) f = filter_val(ax, kx, ky, kz);
-        P.s0[i] = cmul_r(r, f);
-      } break;
-      case CM_ETD_S1: {
-        double2 s0 = P.s0[i];
-        P.n1[i] = Nh;
-        P.s1[i] = cadd(cmul_r(s0, P.E2[crow + ix]), cmul_r(Nh, P.zeta[crow + ix]));
-      } break;
-      case CM_ETD_S2: {
-        P.acc[i] = Nh;
-        P.s2[i] = cadd(cmul_r(P.s0[i], P.E2[crow + ix]), cmul_r(Nh, P.zeta[crow + ix]));
-      } break;
-      case CM_ETD_S3: {
-        P.acc[i] = cadd(P.acc[i], Nh);
-        double2 n1 = P.n1[i];
-        double2 t = make_double2(2 * Nh.x - n1.x, 2 * Nh.y - n1.y);
-        P.s2[i] = cadd(cmul_r(P.s1[i], P.E2[crow + ix]), cmul_r(t, P.zeta[crow + ix]));
-      } break;
-      case CM_ETD_S4: {
-        double2 r = cmul_r(P.s0[i], P.E[crow + ix]);
-        r = cadd(r, cmul_r(P.n1[i], P.alpha[crow + ix]));
-        r = cadd(r, cmul_r(P.acc[i], 2 * P.beta[crow + ix]));
-        r = cadd(r, cmul_r(Nh, P.gamma[crow + ix]));
-        if (A.filtered) f = filter_val(ax, kx, ky, kz);
-        P.s0[i] = cmul_r(r, f);
-      } break;
-      case CM_EULER: {
-        double L = lin_op(ax, kx, ky, kz);
-        double2 s0 = P.s0[i];
-        double2 k = cadd(Nh, cmul_r(s0, L));
-        double2 r = cadd(s0, cmul_r(k, dt));
-        if (A.filtered) f = filter_val(ax, kx, ky, kz);
-        P.s0[i] = cmul_r(r, f);
-      } break;
-      case CM_LSRK: {
-        double L = lin_op(ax, kx, ky, kz);
-        double2 s0 = P.s0[i];
-        double2 k = cadd(Nh, cmul_r(s0, L));
-        double2 S2 = cadd(cmul_r(P.acc[i], A.lsrk_a), cmul_r(k, dt));
-        P.acc[i] = S2;
-        double2 r = cadd(s0, cmul_r(S2, A.lsrk_b));
-        if (A.lsrk_last && A.filtered) {
-          f = filter_val(ax, kx, ky, kz);
-          r = cmul_r(r, f);
-        }
-        P.s0[i] = r;
-      } break;
-      case CM_AB3_EULER:
-      case CM_AB3: {
-        double L = lin_op(ax, kx, ky, kz);
-        double2 s0 = P.s0[i];
-        double2 k = cadd(Nh, cmul_r(s0, L));
-        double2 k1 = P.acc[i], k2 = P.n1[i];
-        double2 inc = k;
-        if (A.mode == CM_AB3) {
-          inc.x = 23.0 / 12.0 * k.x - 16.0 / 12.0 * k1.x + 5.0 / 12.0 * k2.x;
-          inc.y = 23.0 / 12.0 * k.y - 16.0 / 12.0 * k1.y + 5.0 / 12.0 * k2.y;
-        }
-        double2 r = cadd(s0, cmul_r(inc, dt));
-        if (A.filtered) f = filter_val(ax, kx, ky, kz);
-        P.s0[i] = cmul_r(r, f);
-        P.n1[i] = k1;
-        P.acc[i] = k;
-      } break;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// ETDRK4 coefficients (FF getetdcoeffs / getexpLs): 32-point contour mean around dt*L, on device.
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double2 cx_mul(double2 a, double2 b) {
-  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ double2 cx_div(double2 a, double2 b) {
-  double d = b.x * b.x + b.y * b.y;
-  return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
-}
-__device__ __forceinline__ double2 cx_exp(double2 z) {
-  double e = exp(z.x), s, c;
-  sincos(z.y, &s, &c);
-  return make_double2(e * c, e * s);
-}
-
-__global__ void __launch_bounds__(256) k_etd_coeffs(double* E, double* E2, double* zeta, double* alpha, double* beta,
-                                                    double* gamma, AxisTables ax, SpecShape sh, double dt) {
-  int64_t n = sh.nkr * sh.ny * sh.nz;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t ix = i % sh.nkr;
-    int64_t iy = (i / sh.nkr) % sh.ny;
-    int64_t iz = i / (sh.nkr * sh.ny);
-    double L = lin_op(ax, ax.kx[ix], ax.ky[iy], ax.kz[iz]);
-    double Ldt = dt * L;
-    double sz = 0, sa = 0, sb = 0, sg = 0;
-    const int ncirc = 32;
-    for (int j = 0; j < ncirc; ++j) {
-      double s, c;
-      sincospi(2.0 * (j + 0.5) / ncirc, &s, &c);
-      double2 z = make_double2(Ldt + c, s);
-      double2 ez = cx_exp(z);
-      double2 ez2 = cx_exp(make_double2(z.x / 2, z.y / 2));
-      double2 z2 = cx_mul(z, z);
-      double2 z3 = cx_mul(z2, z);
-      // zeta: (exp(z/2)-1)/z
-      sz += cx_div(make_double2(ez2.x - 1.0, ez2.y), z).x;
-      // alpha: (-4 - z + exp(z)(4 - 3z + z^2))/z^3
-      double2 t = cx_mul(ez, make_double2(4.0 - 3.0 * z.x + z2.x, -3.0 * z.y + z2.y));
-      sa += cx_div(make_double2(-4.0 - z.x + t.x, -z.y + t.y), z3).x;
-      // beta: (2 + z + exp(z)(-2 + z))/z^3
-      t = cx_mul(ez, make_double2(-2.0 + z.x, z.y));
-      sb += cx_div(make_double2(2.0 + z.x + t.x, z.y + t.y), z3).x;
-      // gamma: (-4 - 3z - z^2 + exp(z)(4 - z))/z^3
-      t = cx_mul(ez, make_double2(4.0 - z.x, -z.y));
-      sg += cx_div(make_double2(-4.0 - 3.0 * z.x - z2.x + t.x, -3.0 * z.y - z2.y + t.y), z3).x;
-    }
-    E[i] = exp(Ldt);
-    E2[i] = exp(Ldt / 2);
-    zeta[i] = dt * (sz / ncirc);
-    alpha[i] = dt * (sa / ncirc);
-    beta[i] = dt * (sb / ncirc);
-    gamma[i] = dt * (sg / ncirc);
-  }
+  for (int64_t ix = threadIdx.x; ix < sh.nkr; ix += blockDim.x)
+    combine_at(P, A, ax, (size_t)(base + ix), (size_t)(crow + ix), ax.kx[ix], ky, kz, Nh[base + ix]);
 }
 
 // diagnostics: sum of w*|s|^2 (Parseval weights), max |s|, over all members
@@ -394,8 +206,7 @@ class CufftEngine final : public Engine {
     if (base == PTF_STEPPER_ETDRK4) {
       for (auto* b : {&cE, &cE2, &cZ, &cA, &cB, &cG}) b->alloc(g.nspec(), &dev_bytes);
     }
-    va = VelArgs{};
-    va.kind = ctx.d.flow_kind;
+    vs.init(&g, ctx.stream, ctx.d.flow_kind, &dev_bytes);
     make_plans();
     on_dt_changed();
   }
@@ -448,79 +259,18 @@ class CufftEngine final : public Engine {
   }
 
   // ---------------- velocities ----------------
-  void ensure_vel(int comp, int64_t count) {
-    if (vel[comp].n != (size_t)count) {
-      vel[comp].alloc(count, &dev_bytes);
-      drop_graphs();
-    }
-    va.arr[comp] = vel[comp].p;
+  void sync_vel() {
+    if (vs.dirty) drop_graphs();
+    vs.dirty = false;
   }
-
-  void set_velocity(int comp, const double* host, int64_t count) override {
-    PTF_REQUIRE(comp >= 0 && comp < nd, "velocity component out of range");
-    PTF_REQUIRE(count == g.npts() || count == g.npts() * g.B, "velocity count must be npts or npts*nbatch");
-    PTF_REQUIRE(comp == 0 || vel[0].n == 0 || vel[0].n == (size_t)count,
-                "all velocity components must have the same extent");
-    ensure_vel(comp, count);
-    int64_t ms = (count == g.npts() && g.B > 1) ? 0 : g.npts();
-    if (va.member_stride != ms) drop_graphs();
-    va.member_stride = ms;
-    PTF_CUDA(cudaMemcpyAsync(vel[comp].p, host, count * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
-    PTF_CUDA(cudaStreamSynchronize(ctx.stream));
-  }
-
+  void set_velocity(int comp, const double* host, int64_t count) override { vs.set_array(comp, host, count); sync_vel(); }
   void set_velocity_separable(int comp, int nterms, const double* xt, const double* yt, const double* zt,
                               const double* coeff0) override {
-    PTF_REQUIRE(comp >= 0 && comp < nd, "velocity component out of range");
-    PTF_REQUIRE(nterms >= 0 && nterms <= MAX_TERMS, "separable flow supports at most 8 terms per component");
-    SepFlow& f = va.sep[comp];
-    f.nterms = nterms;
-    auto up = [&](DevBuf<double>& b, const double* h, int64_t n) -> const double* {
-      if (!h || nterms == 0) return nullptr;
-      b.alloc((size_t)nterms * n, &dev_bytes);
-      PTF_CUDA(cudaMemcpy(b.p, h, (size_t)nterms * n * sizeof(double), cudaMemcpyHostToDevice));
-      return b.p;
-    };
-    f.xt = up(sepx[comp], xt, g.nx);
-    PTF_REQUIRE(nterms == 0 || f.xt, "separable flow needs an x table");
-    f.yt = nd >= 2 ? up(sepy[comp], yt, g.ny) : nullptr;
-    f.zt = nd >= 3 ? up(sepz[comp], zt, g.nz) : nullptr;
-    PTF_REQUIRE(nterms == 0 || nd < 2 || f.yt, "separable flow needs a y table");
-    PTF_REQUIRE(nterms == 0 || nd < 3 || f.zt, "separable flow needs a z table");
-    if (!sepa.p) {
-      sepa.alloc(3 * MAX_TERMS, &dev_bytes);
-      PTF_CUDA(cudaMemset(sepa.p, 0, sepa.bytes()));
-    }
-    f.a = sepa.p + comp * MAX_TERMS;
-    double a0[MAX_TERMS];
-    for (int m = 0; m < MAX_TERMS; ++m) a0[m] = (m < nterms) ? (coeff0 ? coeff0[m] : 1.0) : 0.0;
-    PTF_CUDA(cudaMemcpy(sepa.p + comp * MAX_TERMS, a0, sizeof(a0), cudaMemcpyHostToDevice));
-    drop_graphs();
+    vs.set_separable(comp, nterms, xt, yt, zt, coeff0);
+    sync_vel();
   }
-
-  void set_velocity_coeffs(int comp, int nterms, const double* a) override {
-    SepFlow& f = va.sep[comp];
-    PTF_REQUIRE(nterms == f.nterms && f.a, "coefficient count does not match the separable flow");
-    // pageable-source async copy: staged before the call returns, ordered on the step stream
-    PTF_CUDA(cudaMemcpyAsync(sepa.p + comp * MAX_TERMS, a, nterms * sizeof(double), cudaMemcpyHostToDevice,
-                             ctx.stream));
-  }
-
-  void set_layered_shift(const double* U) override {
-    if (!U) {
-      if (va.ushift) drop_graphs();
-      va.ushift = nullptr;
-      return;
-    }
-    if (ushift.n != (size_t)(g.B * g.ny)) {
-      ushift.alloc(g.B * g.ny, &dev_bytes);
-      drop_graphs();
-    }
-    PTF_CUDA(cudaMemcpyAsync(ushift.p, U, ushift.bytes(), cudaMemcpyHostToDevice, ctx.stream));
-    PTF_CUDA(cudaStreamSynchronize(ctx.stream));
-    if (va.ushift != ushift.p) drop_graphs();
-    va.ushift = ushift.p;
-  }
+  void set_velocity_coeffs(int comp, int nterms, const double* a) override { vs.set_coeffs(comp, nterms, a); }
+  void set_layered_shift(const double* U) override { vs.set_shift(U); sync_vel(); }
 
   // ---------------- state ----------------
   void set_c(const double* c_host, bool replicate) override {
@@ -559,8 +309,8 @@ class CufftEngine final : public Engine {
   void on_dt_changed() override {
     drop_graphs();
     if (ctx.st.base == PTF_STEPPER_ETDRK4) {
-      k_etd_coeffs<<<flat_blocks(g.nspec()), 256, 0, ctx.stream>>>(cE.p, cE2.p, cZ.p, cA.p, cB.p, cG.p, ctx.ax, shape(),
-                                                                    ctx.dt);
+      k_etd_coeffs<<<flat_blocks(g.nspec()), 256, 0, ctx.stream>>>(cE.p, cE2.p, cZ.p, cA.p, cB.p, cG.p, ctx.ax, g.nkr,
+                                                                    g.ny, g.nz, ctx.dt, 0);
       ++own_launches;
       PTF_CUDA(cudaGetLastError());
     }
@@ -588,11 +338,11 @@ class CufftEngine final : public Engine {
     const double* g1 = nd >= 2 ? gr[1].p : gr[0].p;
     const double* g2 = nd >= 3 ? gr[2].p : gr[0].p;
     if (nd == 1)
-      k_product<1><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nz);
+      k_product<1><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, vs.va, g.nx, g.ny, g.nz);
     else if (nd == 2)
-      k_product<2><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nz);
+      k_product<2><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, vs.va, g.nx, g.ny, g.nz);
     else
-      k_product<3><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nz);
+      k_product<3><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, vs.va, g.nx, g.ny, g.nz);
     ++own_launches;
     PTF_CUFFT(cufftExecD2Z(plan_fwd, gr[0].p, reinterpret_cast<cufftDoubleComplex*>(dh[0].p)));
     ++lib_calls;
@@ -601,9 +351,9 @@ class CufftEngine final : public Engine {
   void combine(int mode, double lsrk_a = 0, double lsrk_b = 0, int lsrk_last = 0) {
     dim3 grid, block;
     spec_launch_dims(grid, block);
-    CombinePtrs P{dh[0].p, sol.p, s1.p, s2.p, acc.p, n1.p, cE.p, cE2.p, cZ.p, cA.p, cB.p, cG.p};
+    CombinePtrs P{sol.p, s1.p, s2.p, acc.p, n1.p, cE.p, cE2.p, cZ.p, cA.p, cB.p, cG.p};
     CombineArgs A{mode, ctx.st.filtered ? 1 : 0, ctx.dt, lsrk_a, lsrk_b, lsrk_last};
-    k_combine<<<grid, block, 0, ctx.stream>>>(P, A, ctx.ax, shape());
+    k_combine<<<grid, block, 0, ctx.stream>>>(dh[0].p, P, A, ctx.ax, shape());
     ++own_launches;
   }
 
@@ -738,10 +488,10 @@ class CufftEngine final : public Engine {
   int nd;
   int64_t nspec, nreal;
   DevBuf<double2> sol, s1, s2, acc, n1, dh[3];
-  DevBuf<double> gr[3], vel[3], sepx[3], sepy[3], sepz[3], sepa, ushift;
+  DevBuf<double> gr[3];
+  VelocityStore vs;
   DevBuf<double> cE, cE2, cZ, cA, cB, cG;
   DevBuf<char> work;
-  VelArgs va;
   cufftHandle plan_fwd = 0, plan_inv = 0;
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
   int64_t per_step_own = 0, per_step_lib = 0;

@@ -505,4 +505,9 @@ int32_t ptf_diag(ptf_handle* h, double* mean_c, double* variance_c, double* max_
   return guarded(h, [&]() { h->engine->diag(mean_c, variance_c, max_abs_sol); });
 }
 
+int32_t ptf_selftest_fft(int32_t n, int32_t dir, int32_t count, const double* in_host, double* out_host) {
+  if (!in_host || !out_host) return PTF_EINVAL;
+  return guarded(nullptr, [&]() { ptf::selftest_fft(n, dir, count, in_host, out_host); });
+}
+
 }  // extern "C"

@@ -151,6 +151,7 @@ struct Context {
 std::unique_ptr<Engine> make_cufft_engine(Context& ctx);
 std::unique_ptr<Engine> make_fused_engine(Context& ctx);  // throws PTF_EUNSUPPORTED when the grid does not qualify
 bool fused_engine_supports(const Context& ctx, std::string* why);
+void selftest_fft(int n, int dir, int count, const double* in_host, double* out_host);
 
 }  // namespace ptf
 
