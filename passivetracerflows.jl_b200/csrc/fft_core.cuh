@@ -105,7 +105,7 @@ PTF_HD constexpr int pad_idx(int i) { return i + (i >> 4); }
 
 // Device-resident twiddle tables for one transform length (forward sign; inverse conjugates on use).
 struct Twiddles {
-  const double2* tw2;  // [15][16]   w_256^(r*k), r = 1..15, k = 0..15
+  const double2* tw2;  // [4][16]    w_256^(2^m * k), m = 0..3, k = 0..15
   const double2* tw3;  // [4][256]   w_N^(2^m * k), m = 0..3, k = 0..255   (unused for N = 256)
 };
 
@@ -127,6 +127,28 @@ PTF_HD constexpr int out_slot(int e) {
                               : e;
 }
 
+// v[r] *= w^r for r = 1..15 given w^1, w^2, w^4, w^8 (forward-sign table values)
+template <int DIR>
+PTF_HD void twiddle15(double2 (&v)[16], double2 w1, double2 w2, double2 w4, double2 w8) {
+  const double2 w3 = cmul2(w1, w2), w5 = cmul2(w4, w1), w6 = cmul2(w4, w2);
+  const double2 w7 = cmul2(w4, w3);
+  v[1] = twmul<DIR>(v[1], w1);
+  v[2] = twmul<DIR>(v[2], w2);
+  v[3] = twmul<DIR>(v[3], w3);
+  v[4] = twmul<DIR>(v[4], w4);
+  v[5] = twmul<DIR>(v[5], w5);
+  v[6] = twmul<DIR>(v[6], w6);
+  v[7] = twmul<DIR>(v[7], w7);
+  v[8] = twmul<DIR>(v[8], w8);
+  v[9] = twmul<DIR>(v[9], cmul2(w8, w1));
+  v[10] = twmul<DIR>(v[10], cmul2(w8, w2));
+  v[11] = twmul<DIR>(v[11], cmul2(w8, w3));
+  v[12] = twmul<DIR>(v[12], cmul2(w8, w4));
+  v[13] = twmul<DIR>(v[13], cmul2(w8, w5));
+  v[14] = twmul<DIR>(v[14], cmul2(w8, w6));
+  v[15] = twmul<DIR>(v[15], cmul2(w8, w7));
+}
+
 #ifdef __CUDACC__
 // One transform by T cooperating threads of a CTA; all 256 threads of the CTA must call it (CTA-wide barriers).
 // `sm` points at this transform's padded buffer; it may be reused by the caller after the call returns AND a barrier.
@@ -143,8 +165,12 @@ __device__ __forceinline__ void fft_cta(double2 (&v)[16], double2* __restrict__ 
   for (int e = 0; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
   // ---- pass 2: radix 16, Ns = 16 ----
   const int k2 = t & 15;
-#pragma unroll
-  for (int r = 1; r < 16; ++r) v[r] = twmul<DIR>(v[r], __ldg(&tw.tw2[(r - 1) * 16 + k2]));
+  {
+    // w_256^(r*k2), r = 1..15, from 4 table entries (r = 1,2,4,8) and at most 3 chained products
+    const double2 w1 = __ldg(&tw.tw2[k2]), w2 = __ldg(&tw.tw2[16 + k2]);
+    const double2 w4 = __ldg(&tw.tw2[32 + k2]), w8 = __ldg(&tw.tw2[48 + k2]);
+    twiddle15<DIR>(v, w1, w2, w4, w8);
+  }
   dft16<DIR>(v);
   if (R3 == 1) return;
   __syncthreads();
@@ -188,23 +214,7 @@ __device__ __forceinline__ void fft_cta(double2 (&v)[16], double2* __restrict__ 
       double2 w2 = __ldg(&tw.tw3[256 + k]);
       double2 w4 = __ldg(&tw.tw3[512 + k]);
       double2 w8 = __ldg(&tw.tw3[768 + k]);
-      double2 w3 = cmul2(w1, w2), w5 = cmul2(w4, w1), w6 = cmul2(w4, w2);
-      double2 w7 = cmul2(w4, w3);
-      v[1] = twmul<DIR>(v[1], w1);
-      v[2] = twmul<DIR>(v[2], w2);
-      v[3] = twmul<DIR>(v[3], w3);
-      v[4] = twmul<DIR>(v[4], w4);
-      v[5] = twmul<DIR>(v[5], w5);
-      v[6] = twmul<DIR>(v[6], w6);
-      v[7] = twmul<DIR>(v[7], w7);
-      v[8] = twmul<DIR>(v[8], w8);
-      v[9] = twmul<DIR>(v[9], cmul2(w8, w1));
-      v[10] = twmul<DIR>(v[10], cmul2(w8, w2));
-      v[11] = twmul<DIR>(v[11], cmul2(w8, w3));
-      v[12] = twmul<DIR>(v[12], cmul2(w8, w4));
-      v[13] = twmul<DIR>(v[13], cmul2(w8, w5));
-      v[14] = twmul<DIR>(v[14], cmul2(w8, w6));
-      v[15] = twmul<DIR>(v[15], cmul2(w8, w7));
+      twiddle15<DIR>(v, w1, w2, w4, w8);
       dft16<DIR>(v);
     }
   }

@@ -106,13 +106,15 @@ struct CombinePtrs {
 // One element of the stage combine.  i = element index in the state arrays, ci = index in the (batch-shared) ETD
 // coefficient arrays, Nh = transformed nonlinear term.  Performs all loads/stores of the FF stepper for this element
 // and returns the state the NEXT calcN is evaluated at (sol_1 / sol_2 / the new sol).
+enum { CMASK_RK4 = 1, CMASK_ETD = 2, CMASK_OTHER = 4, CMASK_ALL = 7 };
+template <int MASK = CMASK_ALL>
 __device__ __forceinline__ double2 combine_at(const CombinePtrs& P, const CombineArgs& A, const AxisTables& ax,
                                               size_t i, size_t ci, double kx, double ky, double kz, double2 Nh) {
   const double dt = A.dt;
   double f = 1.0;
   double2 next = make_double2(0.0, 0.0);
   switch (A.mode) {
-    case CM_RK4_S1: {
+    case CM_RK4_S1: if (MASK & CMASK_RK4) {
       double L = lin_op(ax, kx, ky, kz);
       double2 s0 = P.s0[i];
       double2 k = cadd(Nh, cmul_r(s0, L));
@@ -121,7 +123,7 @@ __device__ __forceinline__ double2 combine_at(const CombinePtrs& P, const Combin
       P.s1[i] = next;
     } break;
     case CM_RK4_S2:
-    case CM_RK4_S3: {
+    case CM_RK4_S3: if (MASK & CMASK_RK4) {
       double L = lin_op(ax, kx, ky, kz);
       double2 ss = P.s1[i];
       double2 k = cadd(Nh, cmul_r(ss, L));
@@ -130,7 +132,7 @@ __device__ __forceinline__ double2 combine_at(const CombinePtrs& P, const Combin
       next = cadd(P.s0[i], cmul_r(k, h));
       P.s1[i] = next;
     } break;
-    case CM_RK4_S4: {
+    case CM_RK4_S4: if (MASK & CMASK_RK4) {
       double L = lin_op(ax, kx, ky, kz);
       double2 ss = P.s1[i];
       double2 k = cadd(Nh, cmul_r(ss, L));
@@ -140,25 +142,25 @@ __device__ __forceinline__ double2 combine_at(const CombinePtrs& P, const Combin
       next = cmul_r(r, f);
       P.s0[i] = next;
     } break;
-    case CM_ETD_S1: {
+    case CM_ETD_S1: if (MASK & CMASK_ETD) {
       double2 s0 = P.s0[i];
       P.n1[i] = Nh;
       next = cadd(cmul_r(s0, P.E2[ci]), cmul_r(Nh, P.zeta[ci]));
       P.s1[i] = next;
     } break;
-    case CM_ETD_S2: {
+    case CM_ETD_S2: if (MASK & CMASK_ETD) {
       P.acc[i] = Nh;
       next = cadd(cmul_r(P.s0[i], P.E2[ci]), cmul_r(Nh, P.zeta[ci]));
       P.s2[i] = next;
     } break;
-    case CM_ETD_S3: {
+    case CM_ETD_S3: if (MASK & CMASK_ETD) {
       P.acc[i] = cadd(P.acc[i], Nh);
       double2 n1 = P.n1[i];
       double2 t = make_double2(2 * Nh.x - n1.x, 2 * Nh.y - n1.y);
       next = cadd(cmul_r(P.s1[i], P.E2[ci]), cmul_r(t, P.zeta[ci]));
       P.s2[i] = next;
     } break;
-    case CM_ETD_S4: {
+    case CM_ETD_S4: if (MASK & CMASK_ETD) {
       double2 r = cmul_r(P.s0[i], P.E[ci]);
       r = cadd(r, cmul_r(P.n1[i], P.alpha[ci]));
       r = cadd(r, cmul_r(P.acc[i], 2 * P.beta[ci]));
@@ -167,7 +169,7 @@ __device__ __forceinline__ double2 combine_at(const CombinePtrs& P, const Combin
       next = cmul_r(r, f);
       P.s0[i] = next;
     } break;
-    case CM_EULER: {
+    case CM_EULER: if (MASK & CMASK_OTHER) {
       double L = lin_op(ax, kx, ky, kz);
       double2 s0 = P.s0[i];
       double2 k = cadd(Nh, cmul_r(s0, L));
@@ -176,7 +178,7 @@ __device__ __forceinline__ double2 combine_at(const CombinePtrs& P, const Combin
       next = cmul_r(r, f);
       P.s0[i] = next;
     } break;
-    case CM_LSRK: {
+    case CM_LSRK: if (MASK & CMASK_OTHER) {
       double L = lin_op(ax, kx, ky, kz);
       double2 s0 = P.s0[i];
       double2 k = cadd(Nh, cmul_r(s0, L));
@@ -191,7 +193,7 @@ __device__ __forceinline__ double2 combine_at(const CombinePtrs& P, const Combin
       P.s0[i] = next;
     } break;
     case CM_AB3_EULER:
-    case CM_AB3: {
+    case CM_AB3: if (MASK & CMASK_OTHER) {
       double L = lin_op(ax, kx, ky, kz);
       double2 s0 = P.s0[i];
       double2 k = cadd(Nh, cmul_r(s0, L));
