@@ -342,35 +342,37 @@ __device__ __forceinline__ void x_nyquist(int t, const double2* Ab, const double
 template <int NX, int VMODE>
 __device__ __forceinline__ void x_request_uv(const XArgs& a, size_t voff, int q, int t, uint32_t t_uv) {
   constexpr int T = Cfg<NX>::T;
+  constexpr int UB = 16;  // velocity request batch
   if (VMODE != 2) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      double2 uv[8];
+    for (int h = 0; h < 16 / UB; ++h) {
+      double2 uv[UB];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const size_t i = voff + (size_t)q * NX + t + T * (8 * h + j);
+      for (int j = 0; j < UB; ++j) {
+        const size_t i = voff + (size_t)q * NX + t + T * (UB * h + j);
         if (a.ablate & 2) uv[j] = make_double2(0.5, 0.25);
         else uv[j] = make_double2(tmem::ldg64(a.va.arr[0] + i), tmem::ldg64(a.va.arr[1] + i));
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) tmem::st1(t_uv + 32 * h + 4 * j, uv[j]);
+      for (int j = 0; j < UB; ++j) tmem::st1(t_uv + 4 * (UB * h + j), uv[j]);
     }
   }
   tmem::wait_st();
 }
 // physical space: v = gx + i*gy at x = t + T*e;  p = -u*gx - v*gy  (TAD.jl:764)
 template <int NX, int VMODE, int Q>
-__device__ __forceinline__ void x_product(const XArgs& a, const double2 (&v)[16], double (&p1)[16],
+__device__ __forceinline__ void x_product(const XArgs& a, const double2 (&v)[16], double2 (&w)[16],
                                           double* __restrict__ ps, int t, uint32_t t_uv, int b, int pair) {
   constexpr int T = Cfg<NX>::T;
   const int row = 2 * pair + Q;
+  constexpr int PB = 4;  // velocity fetch batch
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    double2 uv[4];
-    if (VMODE != 2) tmem::ldn<4>(t_uv + 16 * c, uv);
+  for (int c = 0; c < 16 / PB; ++c) {
+    double2 uv[PB];
+    if (VMODE != 2) tmem::ldn<PB>(t_uv + 4 * PB * c, uv);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = 4 * c + j, x = t + T * e;
+    for (int j = 0; j < PB; ++j) {
+      const int e = PB * c + j, x = t + T * e;
       const double2 g = v[out_slot<NX>(e)];
       double u, vv;
       if (VMODE == 2) {
@@ -382,8 +384,8 @@ __device__ __forceinline__ void x_product(const XArgs& a, const double2 (&v)[16]
         if (VMODE == 1) u += a.va.ushift[b * a.ny + row];
       }
       const double p = -u * g.x - vv * g.y;
-      if (Q == 0) ps[x] = p;
-      else p1[e] = p;
+      if (Q == 0) ps[x] = p;                     // row 0: parked in shared memory while row 1 runs
+      else w[e] = make_double2(ps[x], p);        // row 1: packed with row 0 as p_y + i*p_{y+1} for the forward FFT
     }
   }
 }
@@ -397,6 +399,7 @@ __device__ __forceinline__ void x_product(const XArgs& a, const double2 (&v)[16]
 template <int NX, int VMODE>
 __global__ void __launch_bounds__(256, 2) k_fused_x(XArgs a) {
   constexpr int T = Cfg<NX>::T, F = 256 / T, PADN = Cfg<NX>::PADN, H = NX / 2;
+  constexpr int GB = 4;  // gather batch (k's per batch)
   extern __shared__ double2 smem[];
   __shared__ uint32_t tslot;
   const uint32_t tbase = tmem::alloc_cta<256>(&tslot);
@@ -411,73 +414,68 @@ __global__ void __launch_bounds__(256, 2) k_fused_x(XArgs a) {
   const double2* Ab = a.A + (size_t)b * a.nkr * ny + 2 * pair;
   const double2* Bb = a.Bf + (size_t)b * a.nkr * ny + 2 * pair;
   const size_t voff = (size_t)b * a.va.member_stride + (size_t)(2 * pair) * NX;
-  double p1[16];
   double2 v[16];
 
-  // ---------------- row 0 (and the parking of row 1's inputs) ----------------
+  // row 0's inputs, and the parking of row 1's
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {  // 2 batches of 4 k's: 8 x 256-bit requests in flight per thread
-    double2 A0[4], A1[4], B0[4], B1[4];
+  for (int h = 0; h < 8 / GB; ++h) {  // batches of GB k's: 2*GB 256-bit requests in flight per thread
+    double2 A0[GB], A1[GB], B0[GB], B1[GB];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const size_t gi = (size_t)(t + T * (4 * h + j)) * ny;
+    for (int j = 0; j < GB; ++j) {
+      const size_t gi = (size_t)(t + T * (GB * h + j)) * ny;
       tmem::ldg256(Ab + gi, A0[j], A1[j]);
       tmem::ldg256(Bb + gi, B0[j], B1[j]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      tmem::st1(t_in + 32 * h + 4 * j, A1[j]);
-      tmem::st1(t_in + 32 * h + 16 + 4 * j, B1[j]);
+    for (int j = 0; j < GB; ++j) {
+      tmem::st1(t_in + 8 * (GB * h + j), A1[j]);
+      tmem::st1(t_in + 8 * (GB * h + j) + 4, B1[j]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) x_lower<NX>(v[4 * h + j], 4 * h + j, t, A0[j], B0[j], a.ax.kx, sm);
+    for (int j = 0; j < GB; ++j) x_lower<NX>(v[GB * h + j], GB * h + j, t, A0[j], B0[j], a.ax.kx, sm);
   }
-  x_nyquist<NX>(t, Ab, Bb, ny, 0, a.ax.kx, sm);
-  x_request_uv<NX, VMODE>(a, voff, 0, t, t_uv);  // includes tcgen05.wait::st for the parked inputs as well
-  __syncthreads();
+#pragma unroll 1
+  for (int q = 0; q < 2; ++q) {  // deliberately NOT unrolled: one copy of the inverse transform keeps register
+                                 // pressure (and the instruction footprint) down
+    if (q == 1) {
+      __syncthreads();           // exchange buffer free (row 0's transform readers are done)
 #pragma unroll
-  for (int e = 8; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
-  fft::fft_cta<NX, +1>(v, sm, t, a.tw);
-  x_product<NX, VMODE, 0>(a, v, p1, ps, t, t_uv, b, pair);
-
-  // ---------------- row 1 ----------------
-  x_request_uv<NX, VMODE>(a, voff, 1, t, t_uv);
-  __syncthreads();  // exchange buffer free (row 0's transform readers are done)
+      for (int h = 0; h < 4; ++h) {
+        double2 AB[4];  // (A1, B1) of k-slots 2h, 2h+1
+        tmem::ldn<4>(t_in + 16 * h, AB);
+        x_lower<NX>(v[2 * h], 2 * h, t, AB[0], AB[1], a.ax.kx, sm);
+        x_lower<NX>(v[2 * h + 1], 2 * h + 1, t, AB[2], AB[3], a.ax.kx, sm);
+      }
+    }
+    x_nyquist<NX>(t, Ab, Bb, ny, q, a.ax.kx, sm);
+    x_request_uv<NX, VMODE>(a, voff, q, t, t_uv);  // includes tcgen05.wait::st for the parked inputs as well
+    __syncthreads();
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    double2 A1[4], B1[4];
-    tmem::ldn<4>(t_in + 32 * h, A1);
-    tmem::ldn<4>(t_in + 32 * h + 16, B1);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) x_lower<NX>(v[4 * h + j], 4 * h + j, t, A1[j], B1[j], a.ax.kx, sm);
+    for (int e = 8; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
+    fft::fft_cta<NX, +1>(v, sm, t, a.tw);
+    if (q == 0) x_product<NX, VMODE, 0>(a, v, v, ps, t, t_uv, b, pair);
   }
-  x_nyquist<NX>(t, Ab, Bb, ny, 1, a.ax.kx, sm);
-  __syncthreads();
-#pragma unroll
-  for (int e = 8; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
-  fft::fft_cta<NX, +1>(v, sm, t, a.tw);
-  x_product<NX, VMODE, 1>(a, v, p1, ps, t, t_uv, b, pair);
+  double2 w[16];
+  x_product<NX, VMODE, 1>(a, v, w, ps, t, t_uv, b, pair);
 
   // ---------------- forward transform of the row pair packed as p_y + i*p_{y+1} ----------------
-#pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = make_double2(ps[t + T * e], p1[e]);
-  fft::fft_cta<NX, -1>(v, sm, t, a.tw);
+  fft::fft_cta<NX, -1>(w, sm, t, a.tw);
   __syncthreads();
 #pragma unroll
-  for (int e = 8; e < 16; ++e) sm[pad_idx(t + T * e)] = v[out_slot<NX>(e)];
+  for (int e = 8; e < 16; ++e) sm[pad_idx(t + T * e)] = w[out_slot<NX>(e)];
   __syncthreads();
   double2* P0 = a.Px + ((size_t)b * ny + 2 * pair) * a.nkr;
   double2* P1 = P0 + a.nkr;
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int k = t + T * e;
-    double2 W = v[out_slot<NX>(e)];
+    double2 W = w[out_slot<NX>(e)];
     double2 Wm = (e == 0 && t == 0) ? W : sm[pad_idx(NX - k)];
     __stcg(P0 + k, make_double2(0.5 * (W.x + Wm.x), 0.5 * (W.y - Wm.y)));
     __stcg(P1 + k, make_double2(0.5 * (W.y + Wm.y), 0.5 * (Wm.x - W.x)));
   }
   if (t == 0) {
-    double2 W = v[out_slot<NX>(8)];  // index 8*T = NX/2
+    double2 W = w[out_slot<NX>(8)];  // index 8*T = NX/2
     P0[H] = make_double2(W.x, 0.0);
     P1[H] = make_double2(W.y, 0.0);
   }
@@ -543,6 +541,31 @@ __global__ void __launch_bounds__(256) k_diag_t(const double2* __restrict__ s, i
 }
 
 // ---- stand-alone transform test kernel (ptf_selftest_fft): `count` independent length-N transforms ----
+// experiment: compute-only rate of the transform (REP transforms per load/store)
+template <int N>
+__global__ void __launch_bounds__(256, 2) k_fft_rate_test(const double2* __restrict__ in, double2* __restrict__ out,
+                                                          int count, Twiddles tw, int rep) {
+  constexpr int T = Cfg<N>::T, F = 256 / T, PADN = Cfg<N>::PADN;
+  extern __shared__ double2 smem[];
+  const int grp = threadIdx.x / T, t = threadIdx.x % T;
+  const int id = blockIdx.x * F + grp;
+  const size_t base = (size_t)id * N;
+  double2 v[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = in[base + t + T * e];
+#pragma unroll 1
+  for (int r = 0; r < rep; ++r) {
+    fft::fft_cta<N, -1>(v, smem + grp * PADN, t, tw);
+    double2 w[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) w[e] = v[out_slot<N>(e)];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = make_double2(w[e].x * 0.015625, w[e].y * 0.015625);
+  }
+#pragma unroll
+  for (int e = 0; e < 16; ++e) out[base + t + T * e] = v[e];
+}
+
 template <int N, int DIR>
 __global__ void __launch_bounds__(256, 2) k_fft_test(const double2* __restrict__ in, double2* __restrict__ out,
                                                      int count, Twiddles tw) {
@@ -1168,6 +1191,24 @@ void selftest_fft(int n, int dir, int count, const double* in_host, double* out_
     ms /= reps;
     double gb = 2.0 * (double)total * 16 / 1e9;
     fprintf(stderr, "[selftest_fft] n=%d count=%d  %.4f ms  %.0f GB/s (R+W)\n", n, count, ms, gb / ms * 1e3);
+    if (const char* rp = std::getenv("PTF_SELFTEST_REPEAT")) {
+      int rep = std::atoi(rp);
+      PTF_DISPATCH_N(n, {
+        constexpr int F = 256 / Cfg<NN>::T;
+        size_t sm = y_smem<NN>() + g_smem_pad;
+        int blocks = count / F;
+        allow_smem(k_fft_rate_test<NN>, sm);
+        k_fft_rate_test<NN><<<blocks, 256, sm>>>(in.p, out.p, count, tw.dev(), rep);
+        cudaEventRecord(e0);
+        k_fft_rate_test<NN><<<blocks, 256, sm>>>(in.p, out.p, count, tw.dev(), rep);
+        cudaEventRecord(e1);
+      });
+      cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&ms, e0, e1);
+      double nfft = (double)count * rep;
+      fprintf(stderr, "[selftest_fft] compute-only n=%d: %d x %d transforms in %.4f ms -> %.1f transforms/us (chip), %.0f cycles/transform/SM @1.9GHz\n",
+              n, count, rep, ms, nfft / (ms * 1e3), ms * 1e-3 * 1.9e9 * 148 / nfft);
+    }
     for (int pair = 0; pair < 2; ++pair) {
       cudaEventRecord(e0);
       for (int r = 0; r < reps; ++r) {
