@@ -46,8 +46,7 @@ struct YArgs {
   const double2* pf_c[4];     // complex state columns the combine will read: L2-prefetched at CTA start
   const double* pf_r[4];      // real coefficient columns (ETDRK4), same
   int pf_ahead;               // > 0: also prefetch the P^x gather of the column `pf_ahead` CTAs ahead
-  int ablate;                 // experiment bitmask (timing only): 1 contiguous instead of gathered P^x; 2 skip the
-                              // combine; 4 skip the B transform; 8 skip the A transform
+  int ablate;                 // experiment bitmask (timing only): 1 = contiguous instead of gathered P^x
 };
 
 enum { FAM_RK4 = 0, FAM_ETD = 1, FAM_OTHER = 2 };
@@ -63,12 +62,13 @@ __device__ __noinline__ double filter_slow(double fx, double fy, double f_inner,
   return exp(-f_decay * pow(K - f_inner, f_order));
 }
 
-// ---- RK4 family (FF RK4substeps!/RK4update!), NB elements at a time: all loads of a batch are issued before
-// ---- any store so the memory system sees 3*NB independent 16-byte requests per thread
+// ---- RK4 family (FF RK4substeps!/RK4update!).  N^ (t_nh) and the new stage state s' (t_w) live in TMEM, so a
+// ---- batch of NB elements can have all 3*NB of its 16-byte state loads in flight at once (2 memory round trips
+// ---- per column instead of 4) and nothing accumulates in registers.
 template <int NY, int MODE>
-__device__ __forceinline__ void rk4_stage(const YArgs& a, const double2 (&v)[16], double2 (&w)[16], size_t col, int t,
-                                          double kx, bool active, const double (&fl)[16]) {
-  constexpr int T = Cfg<NY>::T, NB = 4;
+__device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_t t_w, size_t col, int t, double kx,
+                                          bool active, const double (&fl)[16]) {
+  constexpr int T = Cfg<NY>::T, NB = 8;
   const double dt = a.C.dt;
 #pragma unroll
   for (int e0 = 0; e0 < 16; e0 += NB) {
@@ -83,37 +83,43 @@ __device__ __forceinline__ void rk4_stage(const YArgs& a, const double2 (&v)[16]
       }
     }
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const int e = e0 + j, l = t + T * e;
-      const size_t i = col + l;
-      const double ky = a.ax.ky[l];
-      const double L = lin_op(a.ax, kx, ky, 0.0);
-      const double2 Nh = v[out_slot<NY>(e)];
-      double2 next;
-      if (MODE == CM_RK4_S1) {
-        double2 k = cadd(Nh, cmul_r(s0[j], L));
-        next = cadd(s0[j], cmul_r(k, dt / 2));
-        if (active) {
-          __stcg(a.P.acc + i, cdiv_r(k, 6.0));
-          __stcg(a.P.s1 + i, next);
+    for (int j0 = 0; j0 < NB; j0 += 4) {
+      double2 nh[4];
+      tmem::ldn<4>(t_nh + 4 * (e0 + j0), nh);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = j0 + jj, e = e0 + j, l = t + T * e;
+        const size_t i = col + l;
+        const double ky = a.ax.ky[l];
+        const double L = lin_op(a.ax, kx, ky, 0.0);
+        const double2 Nh = nh[jj];
+        double2 next;
+        if (MODE == CM_RK4_S1) {
+          double2 k = cadd(Nh, cmul_r(s0[j], L));
+          next = cadd(s0[j], cmul_r(k, dt / 2));
+          if (active) {
+            __stcg(a.P.acc + i, cdiv_r(k, 6.0));
+            __stcg(a.P.s1 + i, next);
+          }
+        } else if (MODE == CM_RK4_S2 || MODE == CM_RK4_S3) {
+          double2 k = cadd(Nh, cmul_r(ss[j], L));
+          next = cadd(s0[j], cmul_r(k, MODE == CM_RK4_S2 ? dt / 2 : dt));
+          if (active) {
+            __stcg(a.P.acc + i, cadd(ac[j], cdiv_r(k, 3.0)));
+            __stcg(a.P.s1 + i, next);
+          }
+        } else {  // CM_RK4_S4
+          double2 k = cadd(Nh, cmul_r(ss[j], L));
+          double2 sum = cadd(ac[j], cdiv_r(k, 6.0));
+          next = cadd(s0[j], cmul_r(sum, dt));
+          if (a.C.filtered) next = cmul_r(next, fl[e]);
+          if (active) __stcg(a.P.s0 + i, next);
         }
-      } else if (MODE == CM_RK4_S2 || MODE == CM_RK4_S3) {
-        double2 k = cadd(Nh, cmul_r(ss[j], L));
-        next = cadd(s0[j], cmul_r(k, MODE == CM_RK4_S2 ? dt / 2 : dt));
-        if (active) {
-          __stcg(a.P.acc + i, cadd(ac[j], cdiv_r(k, 3.0)));
-          __stcg(a.P.s1 + i, next);
-        }
-      } else {  // CM_RK4_S4
-        double2 k = cadd(Nh, cmul_r(ss[j], L));
-        double2 sum = cadd(ac[j], cdiv_r(k, 6.0));
-        next = cadd(s0[j], cmul_r(sum, dt));
-        if (a.C.filtered) next = cmul_r(next, fl[e]);
-        if (active) __stcg(a.P.s0 + i, next);
+        tmem::st1(t_w + 4 * e, make_double2(next.x * a.inv_n, next.y * a.inv_n));
       }
-      w[e] = make_double2(next.x * a.inv_n, next.y * a.inv_n);
     }
   }
+  tmem::wait_st();
 }
 
 // ---- ETDRK4 family (FF ETDRK4substeps!/ETDRK4update!)
@@ -190,7 +196,15 @@ __device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16]
 template <int NY, int FAM, bool HAS_IN, bool HAS_OUT>
 __global__ void __launch_bounds__(256, 2) k_fused_y(YArgs a) {
   constexpr int T = Cfg<NY>::T, F = 256 / T, PADN = Cfg<NY>::PADN;
+  constexpr bool USE_TMEM = HAS_IN && FAM == FAM_RK4;   // N^ and s' parked in TMEM (see rk4_stage)
   extern __shared__ double2 smem[];
+  __shared__ uint32_t tslot;
+  uint32_t tbase = 0, t_nh = 0, t_w = 0;
+  if (USE_TMEM) {
+    tbase = tmem::alloc_cta<256>(&tslot);
+    t_nh = tmem::warp_addr(tbase, 128);
+    t_w = t_nh + 64;
+  }
   const int grp = threadIdx.x / T, t = threadIdx.x % T;
   const int kr_raw = blockIdx.x * F + grp;
   const bool active = kr_raw < a.nkr;
@@ -240,15 +254,22 @@ __global__ void __launch_bounds__(256, 2) k_fused_y(YArgs a) {
         for (int e = 0; e < 16; ++e) prefetch_l2(P2 + (size_t)(t + T * e) * a.nkr);
       }
     }
-    if (a.ablate & 2) {
+    if (FAM == FAM_RK4) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) w[e] = v[out_slot<NY>(e)];
-    } else if (FAM == FAM_RK4) {
+      for (int e = 0; e < 16; ++e) tmem::st1(t_nh + 4 * e, v[out_slot<NY>(e)]);
+      tmem::wait_st();
       switch (a.C.mode) {
-        case CM_RK4_S1: rk4_stage<NY, CM_RK4_S1>(a, v, w, col, t, kx, active, fl); break;
-        case CM_RK4_S2: rk4_stage<NY, CM_RK4_S2>(a, v, w, col, t, kx, active, fl); break;
-        case CM_RK4_S3: rk4_stage<NY, CM_RK4_S3>(a, v, w, col, t, kx, active, fl); break;
-        default: rk4_stage<NY, CM_RK4_S4>(a, v, w, col, t, kx, active, fl); break;
+        case CM_RK4_S1: rk4_stage<NY, CM_RK4_S1>(a, t_nh, t_w, col, t, kx, active, fl); break;
+        case CM_RK4_S2: rk4_stage<NY, CM_RK4_S2>(a, t_nh, t_w, col, t, kx, active, fl); break;
+        case CM_RK4_S3: rk4_stage<NY, CM_RK4_S3>(a, t_nh, t_w, col, t, kx, active, fl); break;
+        default: rk4_stage<NY, CM_RK4_S4>(a, t_nh, t_w, col, t, kx, active, fl); break;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double2 r4[4];
+        tmem::ldn<4>(t_w + 16 * q, r4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[4 * q + j] = r4[j];
       }
     } else if (FAM == FAM_ETD) {
       switch (a.C.mode) {
@@ -274,27 +295,43 @@ __global__ void __launch_bounds__(256, 2) k_fused_y(YArgs a) {
       w[e] = make_double2(s.x * a.inv_n, s.y * a.inv_n);
     }
   }
-  if (!HAS_OUT) return;
+  if (!HAS_OUT) {
+    if (USE_TMEM) tmem::free_cta<256>(tbase);
+    return;
+  }
 
-  if (!(a.ablate & 8)) fft::fft_cta<NY, +1>(w, sm, t, a.tw);
+  fft::fft_cta<NY, +1>(w, sm, t, a.tw);
   if (active) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) __stcg(a.A + col + t + T * e, w[out_slot<NY>(e)]);
   }
-  if (a.ablate & 4) return;
-  // y-derivative: i*l*s'  (s' re-read from the array this thread just wrote: L2 hit, no DRAM traffic)
+  // y-derivative: i*l*s'
+  if (USE_TMEM) {  // s'/N is still parked in TMEM: no second trip to global memory
 #pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    const int l = t + T * e;
-    double2 s = __ldcg(a.next_state + col + l);
-    double ky = a.ax.ky[l] * a.inv_n;
-    w[e] = make_double2(-ky * s.y, ky * s.x);
+    for (int q = 0; q < 4; ++q) {
+      double2 r4[4];
+      tmem::ldn<4>(t_w + 16 * q, r4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double ky = a.ax.ky[t + T * (4 * q + j)];
+        w[4 * q + j] = make_double2(-ky * r4[j].y, ky * r4[j].x);
+      }
+    }
+  } else {         // s' re-read from the array this thread just wrote: L2 hit, no DRAM traffic
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int l = t + T * e;
+      double2 s = __ldcg(a.next_state + col + l);
+      double ky = a.ax.ky[l] * a.inv_n;
+      w[e] = make_double2(-ky * s.y, ky * s.x);
+    }
   }
   fft::fft_cta<NY, +1>(w, sm, t, a.tw);
   if (active) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) __stcg(a.Bf + col + t + T * e, w[out_slot<NY>(e)]);
   }
+  if (USE_TMEM) tmem::free_cta<256>(tbase);
 }
 
 struct XArgs {
