@@ -6,6 +6,7 @@ All numerics run in libptf_b200.so (hand-written sm_100a CUDA + cuFFT); importin
 built library raises — there is no CPU or PyTorch fallback.
 """
 from . import _capi
+from . import parallel
 from . import tracer_advection_diffusion as TracerAdvectionDiffusion
 from .tracer_advection_diffusion import (B200, Device, OneDAdvectingFlow, Problem, SeparableFlow,
                                          ThreeDAdvectingFlow, TracerProblem, TwoDAdvectingFlow, gridpoints, noflow,

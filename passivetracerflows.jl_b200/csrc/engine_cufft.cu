@@ -6,11 +6,16 @@
 //   D2Z        : cuFFT                                               (TAD.jl:766)
 //   k_combine  : addlinearterm! + substepsol!/update! of the FF steppers in one pass, L/filter in registers
 // The whole step is captured in a CUDA graph.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
 #include "ptf_pointwise.cuh"
 #include "ptf_velocity.cuh"
+
+#ifdef PTF_WITH_NCCL
+#include <nccl.h>
+#endif
 
 namespace ptf {
 
@@ -174,6 +179,25 @@ __global__ void __launch_bounds__(256) k_diag(const double2* __restrict__ s, Spe
   }
 }
 
+// ---- slab transposes (3-D, one process per GPU).  blk = nzl*nyl*nkr complex values go to / come from each peer.
+// pack:   T2[r][zl][jl][kx] = T1[zl][r*nyl + jl][kx]       (after the local 2-D r2c, before the all-to-all)
+// unpack: T1[zl][s*nyl + jl][kx] = T2[s][zl][jl][kx]       (after the all-to-all, before the local 2-D c2r)
+__global__ void __launch_bounds__(256) k_slab_pack(const double2* __restrict__ T1, double2* __restrict__ T2, int64_t nkr,
+                                                   int64_t nyl, int64_t nzl, int64_t P, int unpack) {
+  int64_t ny = nyl * P;
+  int64_t rows = nzl * ny;  // (zl, j) rows of nkr
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    int64_t zl = row / ny, j = row % ny;
+    int64_t r = j / nyl, jl = j % nyl;
+    const int64_t a = (zl * ny + j) * nkr;                    // index in T1
+    const int64_t b = ((r * nzl + zl) * nyl + jl) * nkr;      // index in T2
+    if (!unpack)
+      for (int64_t k = threadIdx.x; k < nkr; k += blockDim.x) T2[b + k] = T1[a + k];
+    else
+      for (int64_t k = threadIdx.x; k < nkr; k += blockDim.x) T2[a + k] = T1[b + k];
+  }
+}
+
 inline int pow2_at_least(int64_t v, int cap) {
   int p = 1;
   while (p < v && p < cap) p <<= 1;
@@ -184,8 +208,12 @@ class CufftEngine final : public Engine {
  public:
   explicit CufftEngine(Context& c) : ctx(c), g(c.g) {
     nd = g.ndim;
-    nspec = g.nspec() * g.B;
-    nreal = g.npts() * g.B;
+    nspec = g.lspec() * g.B;
+    nreal = g.lpts() * g.B;
+    axl = ctx.ax;  // tables as this rank sees them: ky starts at its first spectral row
+    axl.ky = ctx.ax.ky + g.yoff;
+    axl.ay_lo = ctx.ax.ay_lo - g.yoff;
+    axl.ay_hi = ctx.ax.ay_hi - g.yoff;
     int base = ctx.st.base;
     sol.alloc(nspec, &dev_bytes);
     PTF_CUDA(cudaMemsetAsync(sol.p, 0, sol.bytes(), ctx.stream));
@@ -204,7 +232,7 @@ class CufftEngine final : public Engine {
       gr[a].alloc(nreal, &dev_bytes);
     }
     if (base == PTF_STEPPER_ETDRK4) {
-      for (auto* b : {&cE, &cE2, &cZ, &cA, &cB, &cG}) b->alloc(g.nspec(), &dev_bytes);
+      for (auto* b : {&cE, &cE2, &cZ, &cA, &cB, &cG}) b->alloc(g.lspec(), &dev_bytes);
     }
     vs.init(&g, ctx.stream, ctx.d.flow_kind, &dev_bytes);
     make_plans();
@@ -215,6 +243,7 @@ class CufftEngine final : public Engine {
     drop_graphs();
     if (plan_fwd) cufftDestroy(plan_fwd);
     if (plan_inv) cufftDestroy(plan_inv);
+    if (plan_z) cufftDestroy(plan_z);
   }
 
   const char* name() const override { return "cufft"; }
@@ -222,6 +251,10 @@ class CufftEngine final : public Engine {
   cudaStream_t stream() const override { return ctx.stream; }
 
   void make_plans() {
+    if (g.slab) {
+      make_slab_plans();
+      return;
+    }
     long long n[3];
     int rank = nd;
     if (nd == 1) { n[0] = g.nx; }
@@ -242,12 +275,87 @@ class CufftEngine final : public Engine {
     PTF_CUFFT(cufftSetStream(plan_inv, ctx.stream));
   }
 
-  SpecShape shape() const { return SpecShape{g.nkr, g.ny, g.nz, g.B}; }
+  // slab decomposition: local batched 2-D (x,y) transforms over the nzl local planes + strided 1-D z transforms
+  void make_slab_plans() {
+    long long n2[2] = {g.ny, g.nx};
+    long long nz1[1] = {g.nz};
+    long long stride = g.nyl * g.nkr;
+    size_t w[3] = {0, 0, 0};
+    PTF_CUFFT(cufftCreate(&plan_fwd));
+    PTF_CUFFT(cufftCreate(&plan_inv));
+    PTF_CUFFT(cufftCreate(&plan_z));
+    for (cufftHandle pl : {plan_fwd, plan_inv, plan_z}) PTF_CUFFT(cufftSetAutoAllocation(pl, 0));
+    PTF_CUFFT(cufftMakePlanMany64(plan_fwd, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_D2Z, g.nzl, &w[0]));
+    PTF_CUFFT(cufftMakePlanMany64(plan_inv, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2D, g.nzl, &w[1]));
+    PTF_CUFFT(cufftMakePlanMany64(plan_z, 1, nz1, nz1, stride, 1, nz1, stride, 1, CUFFT_Z2Z, stride, &w[2]));
+    size_t wm = std::max(w[0], std::max(w[1], w[2]));
+    work.alloc(wm ? wm : 16, &dev_bytes);
+    for (cufftHandle pl : {plan_fwd, plan_inv, plan_z}) {
+      PTF_CUFFT(cufftSetWorkArea(pl, work.p));
+      PTF_CUFFT(cufftSetStream(pl, ctx.stream));
+    }
+    T1.alloc(nspec, &dev_bytes);
+    T2.alloc(nspec, &dev_bytes);
+  }
+
+  void all_to_all(const double2* send, double2* recv) {
+#ifdef PTF_WITH_NCCL
+    ncclComm_t comm = (ncclComm_t)ctx.nccl_comm;
+    const size_t blk = (size_t)g.nzl * g.nyl * g.nkr;  // complex values per peer
+    auto ck = [](ncclResult_t r, const char* what) {
+      if (r != ncclSuccess) throw Error(PTF_ENCCL, std::string(what) + ": " + ncclGetErrorString(r));
+    };
+    ck(ncclGroupStart(), "ncclGroupStart");
+    for (int r = 0; r < g.P; ++r) {
+      ck(ncclSend(send + (size_t)r * blk, 2 * blk, ncclDouble, r, comm, ctx.stream), "ncclSend");
+      ck(ncclRecv(recv + (size_t)r * blk, 2 * blk, ncclDouble, r, comm, ctx.stream), "ncclRecv");
+    }
+    ck(ncclGroupEnd(), "ncclGroupEnd");
+    ++lib_calls;
+#else
+    (void)send; (void)recv;
+    throw Error(PTF_EUNSUPPORTED, "built without NCCL");
+#endif
+  }
+
+  // forward r2c of this rank's physical slab -> its spectral slab  (unnormalised, FF mul!(., rfftplan, .))
+  void fwd(double* real, double2* spec) {
+    if (!g.slab) {
+      PTF_CUFFT(cufftExecD2Z(plan_fwd, real, reinterpret_cast<cufftDoubleComplex*>(spec)));
+      ++lib_calls;
+      return;
+    }
+    PTF_CUFFT(cufftExecD2Z(plan_fwd, real, reinterpret_cast<cufftDoubleComplex*>(T1.p)));
+    k_slab_pack<<<1184, 256, 0, ctx.stream>>>(T1.p, T2.p, g.nkr, g.nyl, g.nzl, g.P, 0);
+    ++own_launches;
+    all_to_all(T2.p, spec);  // received blocks [s][nzl][nyl][nkr] are exactly [nz][nyl][nkr]
+    PTF_CUFFT(cufftExecZ2Z(plan_z, reinterpret_cast<cufftDoubleComplex*>(spec),
+                           reinterpret_cast<cufftDoubleComplex*>(spec), CUFFT_FORWARD));
+    lib_calls += 2;
+  }
+
+  // inverse c2r (input destroyed), x-axis last as in FFTW/cuFFT c2r; the caller folds in 1/N
+  void inv(double2* spec, double* real) {
+    if (!g.slab) {
+      PTF_CUFFT(cufftExecZ2D(plan_inv, reinterpret_cast<cufftDoubleComplex*>(spec), real));
+      ++lib_calls;
+      return;
+    }
+    PTF_CUFFT(cufftExecZ2Z(plan_z, reinterpret_cast<cufftDoubleComplex*>(spec),
+                           reinterpret_cast<cufftDoubleComplex*>(spec), CUFFT_INVERSE));
+    all_to_all(spec, T2.p);  // chunk r of [nz][nyl][nkr] is the z-range of rank r: no packing on the send side
+    k_slab_pack<<<1184, 256, 0, ctx.stream>>>(T2.p, T1.p, g.nkr, g.nyl, g.nzl, g.P, 1);
+    ++own_launches;
+    PTF_CUFFT(cufftExecZ2D(plan_inv, reinterpret_cast<cufftDoubleComplex*>(T1.p), real));
+    lib_calls += 2;
+  }
+
+  SpecShape shape() const { return SpecShape{g.nkr, g.nyl, g.nz, g.B}; }
 
   void spec_launch_dims(dim3& grid, dim3& block) const {
     int tx = pow2_at_least(g.nkr, 256);
     int ty = 256 / tx;
-    int64_t rows = g.ny * g.nz * g.B;
+    int64_t rows = g.nyl * g.nz * g.B;
     block = dim3(tx, ty, 1);
     grid = dim3((unsigned)((rows + ty - 1) / ty), 1, 1);
   }
@@ -274,7 +382,7 @@ class CufftEngine final : public Engine {
 
   // ---------------- state ----------------
   void set_c(const double* c_host, bool replicate) override {
-    int64_t npts = g.npts();
+    int64_t npts = g.lpts();
     if (replicate && g.B > 1) {
       PTF_CUDA(cudaMemcpyAsync(gr[0].p, c_host, npts * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
       k_replicate<<<flat_blocks(npts), 256, 0, ctx.stream>>>(gr[0].p, npts, g.B);
@@ -282,8 +390,7 @@ class CufftEngine final : public Engine {
     } else {
       PTF_CUDA(cudaMemcpyAsync(gr[0].p, c_host, nreal * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
     }
-    PTF_CUFFT(cufftExecD2Z(plan_fwd, gr[0].p, reinterpret_cast<cufftDoubleComplex*>(sol.p)));
-    ++lib_calls;
+    fwd(gr[0].p, sol.p);
     PTF_CUDA(cudaStreamSynchronize(ctx.stream));
   }
 
@@ -291,8 +398,7 @@ class CufftEngine final : public Engine {
     double scale = 1.0 / (double)g.npts();
     k_scale_copy<<<flat_blocks(nspec), 256, 0, ctx.stream>>>(sol.p, dh[0].p, nspec, scale);
     ++own_launches;
-    PTF_CUFFT(cufftExecZ2D(plan_inv, reinterpret_cast<cufftDoubleComplex*>(dh[0].p), gr[0].p));
-    ++lib_calls;
+    inv(dh[0].p, gr[0].p);
     PTF_CUDA(cudaMemcpyAsync(c_host, gr[0].p, nreal * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
     PTF_CUDA(cudaStreamSynchronize(ctx.stream));
   }
@@ -309,8 +415,8 @@ class CufftEngine final : public Engine {
   void on_dt_changed() override {
     drop_graphs();
     if (ctx.st.base == PTF_STEPPER_ETDRK4) {
-      k_etd_coeffs<<<flat_blocks(g.nspec()), 256, 0, ctx.stream>>>(cE.p, cE2.p, cZ.p, cA.p, cB.p, cG.p, ctx.ax, g.nkr,
-                                                                    g.ny, g.nz, ctx.dt, 0);
+      k_etd_coeffs<<<flat_blocks(g.lspec()), 256, 0, ctx.stream>>>(cE.p, cE2.p, cZ.p, cA.p, cB.p, cG.p, axl, g.nkr,
+                                                                    g.nyl, g.nz, ctx.dt, 0);
       ++own_launches;
       PTF_CUDA(cudaGetLastError());
     }
@@ -323,29 +429,29 @@ class CufftEngine final : public Engine {
     double scale = 1.0 / (double)g.npts();
     SpecShape sh = shape();
     if (nd == 1)
-      k_deriv<1><<<grid, block, 0, ctx.stream>>>(ss, dh[0].p, nullptr, nullptr, ctx.ax, sh, scale);
+      k_deriv<1><<<grid, block, 0, ctx.stream>>>(ss, dh[0].p, nullptr, nullptr, axl, sh, scale);
     else if (nd == 2)
-      k_deriv<2><<<grid, block, 0, ctx.stream>>>(ss, dh[0].p, dh[1].p, nullptr, ctx.ax, sh, scale);
+      k_deriv<2><<<grid, block, 0, ctx.stream>>>(ss, dh[0].p, dh[1].p, nullptr, axl, sh, scale);
     else
-      k_deriv<3><<<grid, block, 0, ctx.stream>>>(ss, dh[0].p, dh[1].p, dh[2].p, ctx.ax, sh, scale);
+      k_deriv<3><<<grid, block, 0, ctx.stream>>>(ss, dh[0].p, dh[1].p, dh[2].p, axl, sh, scale);
     ++own_launches;
-    for (int a = 0; a < nd; ++a) {
-      PTF_CUFFT(cufftExecZ2D(plan_inv, reinterpret_cast<cufftDoubleComplex*>(dh[a].p), gr[a].p));
-      ++lib_calls;
-    }
-    int64_t half = g.npts() / 2;
+    for (int a = 0; a < nd; ++a) inv(dh[a].p, gr[a].p);
+    int64_t half = g.lpts() / 2;
+    VelArgs va = vs.va;
+    if (g.slab)
+      for (int c = 0; c < 3; ++c)
+        if (va.sep[c].zt) va.sep[c].zt += g.zoff;  // separable z tables are global: start at this rank's first plane
     dim3 pg((unsigned)flat_blocks(half), (unsigned)g.B, 1);
     const double* g1 = nd >= 2 ? gr[1].p : gr[0].p;
     const double* g2 = nd >= 3 ? gr[2].p : gr[0].p;
     if (nd == 1)
-      k_product<1><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, vs.va, g.nx, g.ny, g.nz);
+      k_product<1><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nzl);
     else if (nd == 2)
-      k_product<2><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, vs.va, g.nx, g.ny, g.nz);
+      k_product<2><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nzl);
     else
-      k_product<3><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, vs.va, g.nx, g.ny, g.nz);
+      k_product<3><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nzl);
     ++own_launches;
-    PTF_CUFFT(cufftExecD2Z(plan_fwd, gr[0].p, reinterpret_cast<cufftDoubleComplex*>(dh[0].p)));
-    ++lib_calls;
+    fwd(gr[0].p, dh[0].p);
   }
 
   void combine(int mode, double lsrk_a = 0, double lsrk_b = 0, int lsrk_last = 0) {
@@ -353,7 +459,7 @@ class CufftEngine final : public Engine {
     spec_launch_dims(grid, block);
     CombinePtrs P{sol.p, s1.p, s2.p, acc.p, n1.p, cE.p, cE2.p, cZ.p, cA.p, cB.p, cG.p};
     CombineArgs A{mode, ctx.st.filtered ? 1 : 0, ctx.dt, lsrk_a, lsrk_b, lsrk_last};
-    k_combine<<<grid, block, 0, ctx.stream>>>(dh[0].p, P, A, ctx.ax, shape());
+    k_combine<<<grid, block, 0, ctx.stream>>>(dh[0].p, P, A, axl, shape());
     ++own_launches;
   }
 
@@ -429,18 +535,25 @@ class CufftEngine final : public Engine {
 
   void diag(double* mean_c, double* var_c, double* max_abs_sol) override {
     DevBuf<double> out;
-    out.alloc(2);
-    PTF_CUDA(cudaMemsetAsync(out.p, 0, 2 * sizeof(double), ctx.stream));
+    out.alloc(4);
+    PTF_CUDA(cudaMemsetAsync(out.p, 0, 4 * sizeof(double), ctx.stream));
     k_diag<<<flat_blocks(nspec), 256, 0, ctx.stream>>>(sol.p, shape(), g.nx, out.p);
     ++own_launches;
-    double h[2];
-    double2 dc;
+    PTF_CUDA(cudaMemcpyAsync(out.p + 2, sol.p, sizeof(double2), cudaMemcpyDeviceToDevice, ctx.stream));  // DC mode
+#ifdef PTF_WITH_NCCL
+    if (g.slab) {  // spectral rows are spread over the ranks; the DC mode lives on rank 0
+      ncclComm_t comm = (ncclComm_t)ctx.nccl_comm;
+      ncclAllReduce(out.p, out.p, 1, ncclDouble, ncclSum, comm, ctx.stream);
+      ncclAllReduce(out.p + 1, out.p + 1, 1, ncclDouble, ncclMax, comm, ctx.stream);
+      ncclBroadcast(out.p + 2, out.p + 2, 2, ncclDouble, 0, comm, ctx.stream);
+    }
+#endif
+    double h[4];
     PTF_CUDA(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
-    PTF_CUDA(cudaMemcpyAsync(&dc, sol.p, sizeof(dc), cudaMemcpyDeviceToHost, ctx.stream));
     PTF_CUDA(cudaStreamSynchronize(ctx.stream));
     double N = (double)g.npts();
     // member-averaged second moment via Parseval; mean from member 0's DC mode
-    double m = dc.x / N;
+    double m = h[2] / N;
     double msq = h[0] / (N * N) / (double)g.B;
     if (mean_c) *mean_c = m;
     if (var_c) *var_c = msq - m * m;
@@ -492,7 +605,9 @@ class CufftEngine final : public Engine {
   VelocityStore vs;
   DevBuf<double> cE, cE2, cZ, cA, cB, cG;
   DevBuf<char> work;
-  cufftHandle plan_fwd = 0, plan_inv = 0;
+  cufftHandle plan_fwd = 0, plan_inv = 0, plan_z = 0;
+  DevBuf<double2> T1, T2;  // slab transposes
+  AxisTables axl;
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
   int64_t per_step_own = 0, per_step_lib = 0;
 };

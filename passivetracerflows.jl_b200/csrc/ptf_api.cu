@@ -3,6 +3,7 @@
 // wavenumbers with a negative y/z Nyquist) — it is part of the product, computed here, not in any oracle.
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <mutex>
 
 #include "ptf_internal.h"
@@ -16,6 +17,46 @@ using namespace ptf;
 namespace {
 
 thread_local std::string g_create_error;
+
+#ifdef PTF_WITH_NCCL
+// One NCCL communicator per (ncclUniqueId, rank) in the process, shared by every handle created with that id
+// (a unique id can seed ncclCommInitRank only once).
+struct CommEntry {
+  ncclComm_t comm;
+  int refs;
+};
+std::mutex g_comm_mu;
+std::map<std::string, CommEntry> g_comms;
+
+ncclComm_t acquire_comm(const uint8_t id_bytes[128], int nranks, int rank) {
+  std::string key(reinterpret_cast<const char*>(id_bytes), 128);
+  key += ":" + std::to_string(nranks) + ":" + std::to_string(rank);
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  auto it = g_comms.find(key);
+  if (it != g_comms.end()) {
+    it->second.refs++;
+    return it->second.comm;
+  }
+  ncclUniqueId id;
+  std::memcpy(&id, id_bytes, 128);
+  ncclComm_t comm;
+  ncclResult_t r = ncclCommInitRank(&comm, nranks, id, rank);
+  if (r != ncclSuccess) throw Error(PTF_ENCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+  g_comms[key] = CommEntry{comm, 1};
+  return comm;
+}
+
+void release_comm(ncclComm_t comm) {
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  for (auto it = g_comms.begin(); it != g_comms.end(); ++it)
+    if (it->second.comm == comm) {
+      // communicators stay alive for the life of the process once created: a later handle with the same id reuses
+      // them (destroying and re-initialising with a spent id is not possible)
+      if (it->second.refs > 0) it->second.refs--;
+      return;
+    }
+}
+#endif
 
 const char* status_name(int32_t s) {
   switch (s) {
@@ -117,9 +158,18 @@ void build_context(ptf_handle* h, const ptf_desc* d) {
       g.B = d->nbatch / d->nranks;
       g.Boffset = g.B * d->rank;
     } else if (d->decomposition == PTF_DECOMP_SLAB) {
-      throw Error(PTF_EUNSUPPORTED, "slab decomposition is not available in this build yet");
+      PTF_REQUIRE(d->ndim == 3, "slab decomposition is implemented for 3-D problems");
+      PTF_REQUIRE(d->nbatch == 1, "slab decomposition needs nbatch == 1");
+      PTF_REQUIRE(g.ny % d->nranks == 0 && g.nz % d->nranks == 0, "ny and nz must be divisible by nranks");
+      g.slab = true;
+      g.P = d->nranks;
+      g.rank = d->rank;
     }  // PTF_DECOMP_NONE: independent replicas
   }
+  g.nzl = g.slab ? g.nz / g.P : g.nz;
+  g.nyl = g.slab ? g.ny / g.P : g.ny;
+  g.zoff = g.slab ? g.nzl * g.rank : 0;
+  g.yoff = g.slab ? g.nyl * g.rank : 0;
   g.kx = rfft_wavenumbers(g.nx, g.Lx);
   g.ky = d->ndim >= 2 ? fft_wavenumbers(g.ny, g.Ly, d->nyquist_sign) : std::vector<double>{0.0};
   g.kz = d->ndim >= 3 ? fft_wavenumbers(g.nz, g.Lz, d->nyquist_sign) : std::vector<double>{0.0};
@@ -139,6 +189,13 @@ void build_context(ptf_handle* h, const ptf_desc* d) {
   c.t = 0.0;
   c.step = 0;
 
+  if (g.slab) {
+#ifdef PTF_WITH_NCCL
+    c.nccl_comm = acquire_comm(d->nccl_id, d->nranks, d->rank);
+#else
+    throw Error(PTF_EUNSUPPORTED, "built without NCCL");
+#endif
+  }
   upload(c.d_kx, g.kx, &c.table_bytes);
   upload(c.d_ky, g.ky, &c.table_bytes);
   upload(c.d_kz, g.kz, &c.table_bytes);
@@ -177,7 +234,7 @@ void run_velocity_providers(ptf_handle* h) {
   int nd = c.g.ndim;
   if (c.d.flow_kind == PTF_FLOW_CALLBACK) {
     if (!h->vel_fn) throw Error(PTF_EINVAL, "PTF_FLOW_CALLBACK problem stepped without ptf_set_velocity_callback");
-    int64_t count = c.g.npts() * (c.d.velocity_per_batch ? c.g.B : 1);
+    int64_t count = c.g.lpts() * (c.d.velocity_per_batch ? c.g.B : 1);
     for (int a = 0; a < nd; ++a)
       if (!h->pinned_vel[a]) PTF_CUDA(cudaMallocHost((void**)&h->pinned_vel[a], count * sizeof(double)));
     // evaluated at clock.t — the time at the START of the step, for all stages (TAD.jl:701,718,737)
@@ -292,7 +349,7 @@ int32_t ptf_create(const ptf_desc* d, ptf_handle** out) {
     if (want == PTF_ENGINE_FUSED) {
       if (!fused_engine_supports(h->ctx, &why)) throw Error(PTF_EUNSUPPORTED, "fused engine: " + why);
       h->engine = make_fused_engine(h->ctx);
-    } else if (want == PTF_ENGINE_AUTO && fused_engine_supports(h->ctx, &why)) {
+    } else if (want == PTF_ENGINE_AUTO && !h->ctx.g.slab && fused_engine_supports(h->ctx, &why)) {
       h->engine = make_fused_engine(h->ctx);
     } else {
       h->engine = make_cufft_engine(h->ctx);
@@ -319,6 +376,9 @@ int32_t ptf_destroy(ptf_handle* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ctx.stream) cudaStreamDestroy(h->ctx.stream);
+#ifdef PTF_WITH_NCCL
+  if (h->ctx.nccl_comm) release_comm((ncclComm_t)h->ctx.nccl_comm);
+#endif
   delete h;
   return PTF_OK;
 }
@@ -327,10 +387,10 @@ int32_t ptf_local_shape(const ptf_handle* h, int64_t phys_n[4], int64_t spec_n[4
                         int64_t spec_offset[4]) {
   if (!h) return PTF_EINVAL;
   const Geometry& g = h->ctx.g;
-  if (phys_n) { phys_n[0] = g.nx; phys_n[1] = g.ny; phys_n[2] = g.nz; phys_n[3] = g.B; }
-  if (spec_n) { spec_n[0] = g.nkr; spec_n[1] = g.ny; spec_n[2] = g.nz; spec_n[3] = g.B; }
-  if (phys_offset) { phys_offset[0] = phys_offset[1] = phys_offset[2] = 0; phys_offset[3] = g.Boffset; }
-  if (spec_offset) { spec_offset[0] = spec_offset[1] = spec_offset[2] = 0; spec_offset[3] = g.Boffset; }
+  if (phys_n) { phys_n[0] = g.nx; phys_n[1] = g.ny; phys_n[2] = g.nzl; phys_n[3] = g.B; }
+  if (spec_n) { spec_n[0] = g.nkr; spec_n[1] = g.nyl; spec_n[2] = g.nz; spec_n[3] = g.B; }
+  if (phys_offset) { phys_offset[0] = phys_offset[1] = 0; phys_offset[2] = g.zoff; phys_offset[3] = g.Boffset; }
+  if (spec_offset) { spec_offset[0] = 0; spec_offset[1] = g.yoff; spec_offset[2] = 0; spec_offset[3] = g.Boffset; }
   return PTF_OK;
 }
 
@@ -369,7 +429,7 @@ int32_t ptf_set_layered_velocity(ptf_handle* h, const double* u, const double* v
   return guarded(h, [&]() {
     const Geometry& g = h->ctx.g;
     PTF_REQUIRE(g.ndim == 2, "layered velocities are 2-D per layer");
-    int64_t count = g.npts() * g.B;
+    int64_t count = g.lpts() * g.B;
     h->engine->set_velocity(0, u, count);
     h->engine->set_velocity(1, v, count);
     h->engine->set_layered_shift(U);

@@ -74,8 +74,15 @@ struct Geometry {
   int64_t B = 1;                   // local batch (layers / members held by this rank)
   int64_t Bglobal = 1, Boffset = 0;
   double Lx = 0, Ly = 0, Lz = 0;
-  int64_t npts() const { return nx * ny * nz; }   // real points per member
-  int64_t nspec() const { return nkr * ny * nz; } // complex coefficients per member
+  int64_t npts() const { return nx * ny * nz; }   // real points per member (global)
+  int64_t nspec() const { return nkr * ny * nz; } // complex coefficients per member (global)
+  // slab decomposition (3-D, one process per GPU): this rank holds z-planes [zoff, zoff+nzl) of physical fields
+  // and ky-rows [yoff, yoff+nyl) of spectral fields.  Single GPU: nzl = nz, nyl = ny.
+  bool slab = false;
+  int P = 1, rank = 0;
+  int64_t nzl = 1, nyl = 1, zoff = 0, yoff = 0;
+  int64_t lpts() const { return nx * ny * nzl; }    // local real points per member
+  int64_t lspec() const { return nkr * nyl * nz; }  // local complex coefficients per member
   std::vector<double> kx, ky, kz;                 // wavenumbers (kz/ky size 1 == {0} on unused axes)
 };
 
@@ -146,6 +153,7 @@ struct Context {
   int64_t step = 0;
   cudaStream_t stream = nullptr;
   int64_t table_bytes = 0;
+  void* nccl_comm = nullptr;  // ncclComm_t when decomposition == PTF_DECOMP_SLAB
 };
 
 std::unique_ptr<Engine> make_cufft_engine(Context& ctx);

@@ -56,7 +56,8 @@ struct VelocityStore {
 
   void set_array(int comp, const double* host, int64_t count) {
     PTF_REQUIRE(comp >= 0 && comp < g->ndim, "velocity component out of range");
-    PTF_REQUIRE(count == g->npts() || count == g->npts() * g->B, "velocity count must be npts or npts*nbatch");
+    PTF_REQUIRE(count == g->lpts() || count == g->lpts() * g->B,
+                "velocity count must be the local point count (times nbatch for per-member fields)");
     PTF_REQUIRE(comp == 0 || vel[0].n == 0 || vel[0].n == (size_t)count,
                 "all velocity components must have the same extent");
     if (vel[comp].n != (size_t)count) {
@@ -64,7 +65,7 @@ struct VelocityStore {
       dirty = true;
     }
     va.arr[comp] = vel[comp].p;
-    int64_t ms = (count == g->npts() && g->B > 1) ? 0 : g->npts();
+    int64_t ms = (count == g->lpts() && g->B > 1) ? 0 : g->lpts();
     if (va.member_stride != ms) dirty = true;
     va.member_stride = ms;
     PTF_CUDA(cudaMemcpyAsync(vel[comp].p, host, count * sizeof(double), cudaMemcpyHostToDevice, stream));

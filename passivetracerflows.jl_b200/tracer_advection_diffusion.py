@@ -237,6 +237,10 @@ class TracerProblem:
         _capi.check(self._lib.ptf_local_shape(h, pn, sn, po, so), h)
         self.local_nbatch = int(pn[3])
         self.batch_offset = int(po[3])
+        # slab decomposition: this rank owns z-planes [z_offset, z_offset+nz_local) in physical space and
+        # ky-rows [ky_offset, ky_offset+ny_local) in spectral space
+        self.nz_local, self.z_offset = int(pn[2]), int(po[2])
+        self.ny_local, self.ky_offset = int(sn[1]), int(so[1])
         nd = grid.ndim
         lead = (self.local_nbatch,) if self.nbatch > 1 else ()
         self._pshape = lead + tuple(int(pn[a]) for a in reversed(range(nd)))
@@ -292,18 +296,27 @@ class TracerProblem:
             arr = np.ascontiguousarray(arr, dtype=np.float64)
             _capi.check(self._lib.ptf_set_velocity(self._h, a, _capi.as_dp(arr), arr.size), self._h)
 
+    def local_gridpoints(self):
+        """``gridpoints(grid)`` restricted to the z-planes this rank owns (the whole grid on a single GPU)."""
+        pts = gridpoints(self.grid)
+        pts = pts if isinstance(pts, tuple) else (pts,)
+        if self.grid.ndim == 3 and self.nz_local != self.grid.nz:
+            sl = slice(self.z_offset, self.z_offset + self.nz_local)
+            pts = tuple(p[sl] for p in pts)
+        return pts
+
     def _install_velocity_callback(self, funcs):
         grid = self.grid
-        pts = gridpoints(grid)
-        pts = pts if isinstance(pts, tuple) else (pts,)
-        npts = int(np.prod(grid.n))
+        pts = self.local_gridpoints()
+        lshape = pts[0].shape
+        npts = int(np.prod(lshape))
         nd = grid.ndim
 
         def cb(user, t, pu, pv, pw):
             # params.u(x, y, clock.t) on gridpoints (TAD.jl:718) — once per step, t = clock.t
             for a, p in enumerate((pu, pv, pw)[:nd]):
                 out = np.ctypeslib.as_array(p, shape=(npts,))
-                out[:] = np.broadcast_to(np.asarray(funcs[a](*pts, t), dtype=np.float64), grid.pshape).ravel()
+                out[:] = np.broadcast_to(np.asarray(funcs[a](*pts, t), dtype=np.float64), lshape).ravel()
 
         fn = _capi.VELOCITY_FN(cb)
         self._keep.append(fn)
@@ -361,7 +374,7 @@ class TracerProblem:
         c = np.ascontiguousarray(c, dtype=np.float64)
         nd = self.grid.ndim
         replicate = self.nbatch > 1 and c.ndim == nd
-        expect = self.grid.pshape if replicate or self.nbatch == 1 else self._pshape
+        expect = self._pshape[-nd:] if replicate or self.nbatch == 1 else self._pshape
         if tuple(c.shape) != tuple(expect):
             raise ValueError(f"c has shape {c.shape}, expected {expect}")
         _capi.check(self._lib.ptf_set_c(self._h, _capi.as_dp(c), 1 if replicate else 0), self._h)
@@ -456,13 +469,12 @@ def Problem(dev_or_mqg, advecting_flow=None, *, nx=128, Lx=2 * math.pi, ny=None,
         prob._install_separable(flow)
         return prob
     funcs = [flow.u, getattr(flow, "v", None), getattr(flow, "w", None)][:nd]
-    pts = gridpoints(grid)
-    pts = pts if isinstance(pts, tuple) else (pts,)
     if flow.steadyflow:
         # ConstDiffSteadyFlowParams: u.(x, y) evaluated ONCE on gridpoints (TAD.jl:426-452)
         prob = TracerProblem(dev, grid, params, dt, stepper, _capi.FLOW_STEADY, nbatch=nbatch,
                              dealias=dealias, aliased_fraction=aliased_fraction, nyquist_sign=nyquist_sign)
-        arrays = [_sample(f, pts, grid.pshape) for f in funcs]
+        pts = prob.local_gridpoints()      # this rank's z-slab (everything on a single GPU)
+        arrays = [_sample(f, pts, pts[0].shape) for f in funcs]
         params.u, params.v, params.w = (arrays + [None, None])[:3]
         prob._set_velocity_arrays(arrays)
     else:
