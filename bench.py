@@ -173,6 +173,69 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_slab3d(args, rank, world, local_rank, P, dist, barrier, max_over_ranks):
+    """BASELINE configs[3]: 3-D prescribed time-dependent (ABC-type, separable) flow, n^3 fp64 with hyperdiffusion,
+    slab-decomposed across the GPUs; the NCCL all-to-all transpose is the only collective.  Strong scaling."""
+    n = args.n3
+    L = 2 * np.pi
+    A, B, Cc = 1.0, 0.8, 0.6
+    one = lambda s: 1.0 + 0 * s
+    g = lambda t: 1.0 + 0.5 * np.sin(t)
+    flow = P.SeparableFlow(
+        terms=[[(one, one, np.sin), (one, np.cos, one)],      # u = (A sin z + C cos y) g(t)
+               [(np.sin, one, one), (one, one, np.cos)],      # v = (B sin x + A cos z) g(t)
+               [(one, np.sin, one), (np.cos, one, one)]],     # w = (C sin y + B cos x) g(t)
+        coeffs=lambda t, a: g(t) * np.array([[A, Cc], [B, A], [Cc, B]][a]),
+        steadyflow=False)
+    kmax2 = 3 * (n / 2) ** 2
+    kappa_h = 1e-3 / kmax2          # hyperdiffusion (n_kappa_h = 2): max|L| = kappa_h * kmax2^2
+    dt = min(0.5 * 2.785 / (kappa_h * kmax2 ** 2), 0.5 * 2.83 / (3 * 1.5 * 1.8 * n / 2))
+    dev = P.parallel.init_b200("slab", device=local_rank) if world > 1 else P.B200(device=local_rank)
+    prob = P.Problem(dev, flow, nx=n, kappa=0.0, dt=dt, stepper=args.stepper, kappa_h=kappa_h, n_kappa_h=2)
+    x = prob.grid.x
+    zs = x[prob.z_offset:prob.z_offset + prob.nz_local]
+    sig = 0.1 * 8                   # resolved Gaussian
+    c0 = np.exp(-(x[None, None, :] ** 2 + x[None, :, None] ** 2 + zs[:, None, None] ** 2) / (2 * sig ** 2))
+    prob.set_c(np.ascontiguousarray(c0))
+    for _ in range(args.warmup):
+        prob.stepforward(1)
+    own0, lib0 = prob.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_ms = prob.step_timed(args.steps)
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join()
+    own1, lib1 = prob.launch_count()
+    dev_ms = max_over_ranks(dev_ms)
+    npts = n ** 3
+    value = npts * args.steps / (dev_ms * 1e-3)
+    d = prob.diagnostics()
+    peak, peak_src = peaks()
+    balg = b_alg(3, args.stepper) - 32 * 3      # velocities generated in registers: -32*d (SURVEY 8d)
+    step_ms = dev_ms / args.steps
+    # per-GPU NVLink floor: each transposed field moves (P-1)/P of the local spectral slab out of every GPU
+    spec_local = (n // 2 + 1) * n * n * 16 / world
+    a2a_bytes = 16 * spec_local * (world - 1) / world if world > 1 else 0
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"slab3d_{n}^3_{args.stepper}_hyperdiffusion_separable_ABC_flow (BASELINE configs[3])",
+                           "n": n, "stepper": args.stepper, "dt": dt, "engine": prob.engine,
+                           "decomposition": "z-slabs (physical) / ky-slabs (spectral), NCCL all-to-all per transform",
+                           "state_finite": bool(np.isfinite(d["max_abs_sol"])), "l2": "fields larger than L2"},
+                "gpu_launches": own1 - own0, "library_calls": lib1 - lib0,
+                "step_roofline": {"b_alg_bytes_per_point_step": balg, "achieved": balg * npts / (step_ms * 1e-3) / 1e9,
+                                  "peak": peak * world, "unit": "GB/s",
+                                  "frac": balg * npts / (step_ms * 1e-3) / 1e9 / (peak * world)},
+                "nvlink": {"alltoall_bytes_out_per_gpu_per_step": a2a_bytes,
+                           "floor_ms_per_step_at_770GBs": a2a_bytes / 770e9 * 1e3},
+                "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,6 +246,10 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "cufft", "fused"])
     ap.add_argument("--stepper", default="RK4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cellular2d", choices=["cellular2d", "slab3d"],
+                    help="cellular2d: BASELINE configs[1], one problem per GPU (default, the graded line); "
+                         "slab3d: BASELINE configs[3], ONE n^3 problem slab-decomposed over all GPUs (strong scaling)")
+    ap.add_argument("--n3", type=int, default=512, help="grid size of the slab3d workload (n^3)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -224,6 +291,12 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    if args.workload == "slab3d":
+        run_slab3d(args, rank, world, local_rank, P, dist, barrier, max_over_ranks)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     w = workload(args.nx)
     nx = w["nx"]

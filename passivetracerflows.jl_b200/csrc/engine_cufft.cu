@@ -8,6 +8,7 @@
 // The whole step is captured in a CUDA graph.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "ptf_pointwise.cuh"
@@ -52,6 +53,45 @@ __global__ void __launch_bounds__(256) k_deriv(double2* __restrict__ s, double2*
     d0[base + ix] = make_double2(-kx * v.y, kx * v.x);
     if (ND >= 2) d1[base + ix] = make_double2(-ky * v.y, ky * v.x);
     if (ND >= 3) d2[base + ix] = make_double2(-kz * v.y, kz * v.x);
+  }
+}
+
+// slab path, step 1 of the shared partial inverse transforms: only TWO fields cross the network,
+//   d0 = s*scale  and  d2 = i*kz*s*scale   (layout [kz][ky_local][kx]); optional dealias!(s) in place first.
+__global__ void __launch_bounds__(256) k_deriv_z(double2* __restrict__ s, double2* __restrict__ d0,
+                                                 double2* __restrict__ d2, AxisTables ax, SpecShape sh, double scale) {
+  int64_t row = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+  int64_t nrows = sh.ny * sh.nz * sh.B;
+  if (row >= nrows) return;
+  int64_t iy = row % sh.ny;
+  int64_t iz = (row / sh.ny) % sh.nz;
+  double kz = ax.kz[iz] * scale;
+  int64_t base = row * sh.nkr;
+  for (int64_t ix = threadIdx.x; ix < sh.nkr; ix += blockDim.x) {
+    double2 v = s[base + ix];
+    if (ax.dealias && dealiased_out(ax, ix, iy, iz)) {
+      v = make_double2(0.0, 0.0);
+      s[base + ix] = v;
+    }
+    d0[base + ix] = make_double2(v.x * scale, v.y * scale);
+    d2[base + ix] = make_double2(-kz * v.y, kz * v.x);
+  }
+}
+
+// slab path, step 2: after the transpose the field is [z_local][ky (all)][kx]; the x and y derivatives are applied
+// here (i*kx in place, i*ky into `dy`), so they never travel.
+__global__ void __launch_bounds__(256) k_deriv_xy_planes(double2* __restrict__ f, double2* __restrict__ dy,
+                                                         const double* __restrict__ kxt, const double* __restrict__ kyt,
+                                                         int64_t nkr, int64_t ny, int64_t nzl) {
+  int64_t row = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+  if (row >= ny * nzl) return;
+  const double ky = kyt[row % ny];
+  int64_t base = row * nkr;
+  for (int64_t ix = threadIdx.x; ix < nkr; ix += blockDim.x) {
+    double2 v = f[base + ix];
+    double kx = kxt[ix];
+    f[base + ix] = make_double2(-kx * v.y, kx * v.x);
+    dy[base + ix] = make_double2(-ky * v.y, ky * v.x);
   }
 }
 
@@ -183,11 +223,12 @@ __global__ void __launch_bounds__(256) k_diag(const double2* __restrict__ s, Spe
 // pack:   T2[r][zl][jl][kx] = T1[zl][r*nyl + jl][kx]       (after the local 2-D r2c, before the all-to-all)
 // unpack: T1[zl][s*nyl + jl][kx] = T2[s][zl][jl][kx]       (after the all-to-all, before the local 2-D c2r)
 __global__ void __launch_bounds__(256) k_slab_pack(const double2* __restrict__ T1, double2* __restrict__ T2, int64_t nkr,
-                                                   int64_t nyl, int64_t nzl, int64_t P, int unpack) {
+                                                   int64_t nyl, int64_t nzl, int64_t P, int unpack, int64_t z0,
+                                                   int64_t nzc) {
   int64_t ny = nyl * P;
-  int64_t rows = nzl * ny;  // (zl, j) rows of nkr
+  int64_t rows = nzc * ny;  // (zl, j) rows of nkr, planes z0 .. z0+nzc-1
   for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-    int64_t zl = row / ny, j = row % ny;
+    int64_t zl = z0 + row / ny, j = row % ny;
     int64_t r = j / nyl, jl = j % nyl;
     const int64_t a = (zl * ny + j) * nkr;                    // index in T1
     const int64_t b = ((r * nzl + zl) * nyl + jl) * nkr;      // index in T2
@@ -203,6 +244,46 @@ inline int pow2_at_least(int64_t v, int cap) {
   while (p < v && p < cap) p <<= 1;
   return p;
 }
+
+// Optional per-phase device timing of the slab path (PTF_SLAB_PROFILE=1; disables graph capture): CUDA events around
+// every phase on the step stream, summed and printed when the engine is destroyed.
+struct PhaseTimer {
+  bool on = false;
+  cudaStream_t st = nullptr;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev;
+  const char* names[6] = {"fft2d", "pack", "alltoall", "fftz", "pointwise", "other"};
+  void begin(int id) {
+    if (!on) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+    ev.push_back({id, {a, b}});
+  }
+  void end() {
+    if (!on) return;
+    cudaEventRecord(ev.back().second.second, st);
+  }
+  void report(int rank) {
+    if (!on || ev.empty()) return;
+    cudaStreamSynchronize(st);
+    double tot[6] = {0};
+    int cnt[6] = {0};
+    for (auto& e : ev) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+      tot[e.first] += ms;
+      cnt[e.first]++;
+      cudaEventDestroy(e.second.first);
+      cudaEventDestroy(e.second.second);
+    }
+    fprintf(stderr, "[slab profile rank %d]", rank);
+    for (int i = 0; i < 6; ++i)
+      if (cnt[i]) fprintf(stderr, "  %s: %.2f ms in %d calls (%.3f ms each)", names[i], tot[i], cnt[i], tot[i] / cnt[i]);
+    fprintf(stderr, "\n");
+    ev.clear();
+  }
+};
 
 class CufftEngine final : public Engine {
  public:
@@ -235,15 +316,23 @@ class CufftEngine final : public Engine {
       for (auto* b : {&cE, &cE2, &cZ, &cA, &cB, &cG}) b->alloc(g.lspec(), &dev_bytes);
     }
     vs.init(&g, ctx.stream, ctx.d.flow_kind, &dev_bytes);
+    pt.st = ctx.stream;
+    pt.on = g.slab && std::getenv("PTF_SLAB_PROFILE") != nullptr;
+    if (pt.on) ctx.d.use_graph = 0;
     make_plans();
     on_dt_changed();
   }
 
   ~CufftEngine() override {
+    pt.report(g.rank);
     drop_graphs();
     if (plan_fwd) cufftDestroy(plan_fwd);
     if (plan_inv) cufftDestroy(plan_inv);
     if (plan_z) cufftDestroy(plan_z);
+    if (plan_fwd_chunk) cufftDestroy(plan_fwd_chunk);
+    if (s_comm) cudaStreamDestroy(s_comm);
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
   }
 
   const char* name() const override { return "cufft"; }
@@ -296,19 +385,55 @@ class CufftEngine final : public Engine {
     }
     T1.alloc(nspec, &dev_bytes);
     T2.alloc(nspec, &dev_bytes);
+    // pipeline resources
+    const char* pe = std::getenv("PTF_SLAB_PIPELINE");
+    slab_pipeline = !(pe && std::atoi(pe) == 0) && nd == 3 && !pt.on;
+    if (slab_pipeline) {
+      n_chunks = 4;
+      while (n_chunks > 1 && g.nzl % n_chunks) n_chunks >>= 1;
+      if (const char* ce = std::getenv("PTF_SLAB_CHUNKS")) {
+        int c = std::atoi(ce);
+        if (c >= 1 && c <= 8 && g.nzl % c == 0) n_chunks = c;
+      }
+      T3.alloc(nspec, &dev_bytes);
+      {  // highest priority: the exchange kernels must get SMs while transforms of the other field are running
+        int lo = 0, hi = 0;
+        PTF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PTF_CUDA(cudaStreamCreateWithPriority(&s_comm, cudaStreamNonBlocking, hi));
+      }
+      for (auto& e : ev) PTF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      size_t wc = 0;
+      PTF_CUFFT(cufftCreate(&plan_fwd_chunk));
+      PTF_CUFFT(cufftSetAutoAllocation(plan_fwd_chunk, 0));
+      PTF_CUFFT(cufftMakePlanMany64(plan_fwd_chunk, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_D2Z, g.nzl / n_chunks, &wc));
+      if (wc > work.bytes()) {
+        work.alloc(wc, &dev_bytes);
+        for (cufftHandle pl : {plan_fwd, plan_inv, plan_z}) PTF_CUFFT(cufftSetWorkArea(pl, work.p));
+      }
+      PTF_CUFFT(cufftSetWorkArea(plan_fwd_chunk, work.p));
+      PTF_CUFFT(cufftSetStream(plan_fwd_chunk, ctx.stream));
+    }
   }
 
-  void all_to_all(const double2* send, double2* recv) {
+  // Exchange of planes [z0, z0+nzc) of every peer block (the whole block by default) on stream `st`.
+  void all_to_all(const double2* send, double2* recv, cudaStream_t st = nullptr, int64_t z0 = 0, int64_t nzc = -1) {
 #ifdef PTF_WITH_NCCL
+    if (!st) st = ctx.stream;
+    if (nzc < 0) nzc = g.nzl;
     ncclComm_t comm = (ncclComm_t)ctx.nccl_comm;
     const size_t blk = (size_t)g.nzl * g.nyl * g.nkr;  // complex values per peer
+    const size_t off = (size_t)z0 * g.nyl * g.nkr, cnt = (size_t)nzc * g.nyl * g.nkr;
     auto ck = [](ncclResult_t r, const char* what) {
       if (r != ncclSuccess) throw Error(PTF_ENCCL, std::string(what) + ": " + ncclGetErrorString(r));
     };
+    // own block: plain device copy; the P-1 peer blocks: one grouped send/recv each over NVLink
+    PTF_CUDA(cudaMemcpyAsync(recv + (size_t)g.rank * blk + off, send + (size_t)g.rank * blk + off,
+                             cnt * sizeof(double2), cudaMemcpyDeviceToDevice, st));
     ck(ncclGroupStart(), "ncclGroupStart");
     for (int r = 0; r < g.P; ++r) {
-      ck(ncclSend(send + (size_t)r * blk, 2 * blk, ncclDouble, r, comm, ctx.stream), "ncclSend");
-      ck(ncclRecv(recv + (size_t)r * blk, 2 * blk, ncclDouble, r, comm, ctx.stream), "ncclRecv");
+      if (r == g.rank) continue;
+      ck(ncclSend(send + (size_t)r * blk + off, 2 * cnt, ncclDouble, r, comm, st), "ncclSend");
+      ck(ncclRecv(recv + (size_t)r * blk + off, 2 * cnt, ncclDouble, r, comm, st), "ncclRecv");
     }
     ck(ncclGroupEnd(), "ncclGroupEnd");
     ++lib_calls;
@@ -325,12 +450,20 @@ class CufftEngine final : public Engine {
       ++lib_calls;
       return;
     }
+    pt.begin(0);
     PTF_CUFFT(cufftExecD2Z(plan_fwd, real, reinterpret_cast<cufftDoubleComplex*>(T1.p)));
-    k_slab_pack<<<1184, 256, 0, ctx.stream>>>(T1.p, T2.p, g.nkr, g.nyl, g.nzl, g.P, 0);
+    pt.end();
+    pt.begin(1);
+    k_slab_pack<<<1184, 256, 0, ctx.stream>>>(T1.p, T2.p, g.nkr, g.nyl, g.nzl, g.P, 0, 0, g.nzl);
+    pt.end();
     ++own_launches;
+    pt.begin(2);
     all_to_all(T2.p, spec);  // received blocks [s][nzl][nyl][nkr] are exactly [nz][nyl][nkr]
+    pt.end();
+    pt.begin(3);
     PTF_CUFFT(cufftExecZ2Z(plan_z, reinterpret_cast<cufftDoubleComplex*>(spec),
                            reinterpret_cast<cufftDoubleComplex*>(spec), CUFFT_FORWARD));
+    pt.end();
     lib_calls += 2;
   }
 
@@ -341,12 +474,20 @@ class CufftEngine final : public Engine {
       ++lib_calls;
       return;
     }
+    pt.begin(3);
     PTF_CUFFT(cufftExecZ2Z(plan_z, reinterpret_cast<cufftDoubleComplex*>(spec),
                            reinterpret_cast<cufftDoubleComplex*>(spec), CUFFT_INVERSE));
+    pt.end();
+    pt.begin(2);
     all_to_all(spec, T2.p);  // chunk r of [nz][nyl][nkr] is the z-range of rank r: no packing on the send side
-    k_slab_pack<<<1184, 256, 0, ctx.stream>>>(T2.p, T1.p, g.nkr, g.nyl, g.nzl, g.P, 1);
+    pt.end();
+    pt.begin(1);
+    k_slab_pack<<<1184, 256, 0, ctx.stream>>>(T2.p, T1.p, g.nkr, g.nyl, g.nzl, g.P, 1, 0, g.nzl);
+    pt.end();
     ++own_launches;
+    pt.begin(0);
     PTF_CUFFT(cufftExecZ2D(plan_inv, reinterpret_cast<cufftDoubleComplex*>(T1.p), real));
+    pt.end();
     lib_calls += 2;
   }
 
@@ -422,8 +563,83 @@ class CufftEngine final : public Engine {
     }
   }
 
+  // ---------------- slab path: one stage with shared partial transforms + comm/compute overlap ----------------
+  // inverse: only s and i*kz*s are z-transformed and transposed (2 all-to-alls); the x/y derivatives are applied in
+  // the plane layout afterwards.  The all-to-alls run on `s_comm` and overlap the other field's transforms.
+  // forward: the 2-D r2c + pack run in NCH plane chunks, each chunk's exchange overlapping the next chunk's FFT.
+  void fork_comm_after(cudaEvent_t e) {  // s_comm waits for everything enqueued on the main stream so far
+    PTF_CUDA(cudaEventRecord(e, ctx.stream));
+    PTF_CUDA(cudaStreamWaitEvent(s_comm, e, 0));
+  }
+  void join_comm(cudaEvent_t e) {        // the main stream waits for everything enqueued on s_comm so far
+    PTF_CUDA(cudaEventRecord(e, s_comm));
+    PTF_CUDA(cudaStreamWaitEvent(ctx.stream, e, 0));
+  }
+
+  void calcN_slab(double2* ss) {
+    dim3 grid, block;
+    spec_launch_dims(grid, block);
+    const double scale = 1.0 / (double)g.npts();
+    auto Z = [](double2* p) { return reinterpret_cast<cufftDoubleComplex*>(p); };
+    k_deriv_z<<<grid, block, 0, ctx.stream>>>(ss, dh[0].p, dh[2].p, axl, shape(), scale);
+    ++own_launches;
+    // field 0 (s): z transform, then its exchange starts on the comm stream
+    PTF_CUFFT(cufftExecZ2Z(plan_z, Z(dh[0].p), Z(dh[0].p), CUFFT_INVERSE));
+    fork_comm_after(ev[0]);
+    all_to_all(dh[0].p, T2.p, s_comm);
+    PTF_CUDA(cudaEventRecord(ev[1], s_comm));
+    // field 2 (i*kz*s): z transform overlaps exchange 0; its exchange then overlaps the plane work of field 0
+    PTF_CUFFT(cufftExecZ2Z(plan_z, Z(dh[2].p), Z(dh[2].p), CUFFT_INVERSE));
+    fork_comm_after(ev[2]);
+    all_to_all(dh[2].p, T3.p, s_comm);
+    PTF_CUDA(cudaEventRecord(ev[3], s_comm));
+    // field 0 arrived: unpack, x/y derivatives in the plane layout, two batched 2-D c2r
+    PTF_CUDA(cudaStreamWaitEvent(ctx.stream, ev[1], 0));
+    k_slab_pack<<<1184, 256, 0, ctx.stream>>>(T2.p, T1.p, g.nkr, g.nyl, g.nzl, g.P, 1, 0, g.nzl);
+    {
+      int tx = pow2_at_least(g.nkr, 256), ty = 256 / tx;
+      dim3 b2(tx, ty, 1), g2((unsigned)((g.ny * g.nzl + ty - 1) / ty), 1, 1);
+      k_deriv_xy_planes<<<g2, b2, 0, ctx.stream>>>(T1.p, dh[1].p, ctx.ax.kx, ctx.ax.ky, g.nkr, g.ny, g.nzl);
+    }
+    own_launches += 2;
+    PTF_CUFFT(cufftExecZ2D(plan_inv, Z(T1.p), gr[0].p));
+    PTF_CUFFT(cufftExecZ2D(plan_inv, Z(dh[1].p), gr[1].p));
+    // field 2 arrived
+    PTF_CUDA(cudaStreamWaitEvent(ctx.stream, ev[3], 0));
+    k_slab_pack<<<1184, 256, 0, ctx.stream>>>(T3.p, T1.p, g.nkr, g.nyl, g.nzl, g.P, 1, 0, g.nzl);
+    ++own_launches;
+    PTF_CUFFT(cufftExecZ2D(plan_inv, Z(T1.p), gr[2].p));
+    lib_calls += 7;
+    // physical-space product
+    int64_t half = g.lpts() / 2;
+    dim3 pg((unsigned)flat_blocks(half), (unsigned)g.B, 1);
+    VelArgs va = vs.va;
+    for (int c = 0; c < 3; ++c)
+      if (va.sep[c].zt) va.sep[c].zt += g.zoff;
+    k_product<3><<<pg, 256, 0, ctx.stream>>>(gr[0].p, gr[1].p, gr[2].p, va, g.nx, g.ny, g.nzl);
+    ++own_launches;
+    // forward: chunked 2-D r2c + pack, exchanges pipelined on the comm stream, then the z transform
+    const int nch = n_chunks;
+    const int64_t nzc = g.nzl / nch;
+    for (int c = 0; c < nch; ++c) {
+      const int64_t z0 = c * nzc;
+      PTF_CUFFT(cufftExecD2Z(plan_fwd_chunk, gr[0].p + z0 * g.nx * g.ny, Z(T1.p + z0 * g.ny * g.nkr)));
+      k_slab_pack<<<1184, 256, 0, ctx.stream>>>(T1.p, T2.p, g.nkr, g.nyl, g.nzl, g.P, 0, z0, nzc);
+      ++own_launches;
+      fork_comm_after(ev[4 + c]);
+      all_to_all(T2.p, dh[0].p, s_comm, z0, nzc);
+    }
+    join_comm(ev[4 + nch]);
+    PTF_CUFFT(cufftExecZ2Z(plan_z, Z(dh[0].p), Z(dh[0].p), CUFFT_FORWARD));
+    lib_calls += nch + 1;
+  }
+
   // ---------------- one stage: N-hat(ss) into dh[0] ----------------
   void calcN(double2* ss) {
+    if (g.slab && slab_pipeline) {
+      calcN_slab(ss);
+      return;
+    }
     dim3 grid, block;
     spec_launch_dims(grid, block);
     double scale = 1.0 / (double)g.npts();
@@ -436,6 +652,7 @@ class CufftEngine final : public Engine {
       k_deriv<3><<<grid, block, 0, ctx.stream>>>(ss, dh[0].p, dh[1].p, dh[2].p, axl, sh, scale);
     ++own_launches;
     for (int a = 0; a < nd; ++a) inv(dh[a].p, gr[a].p);
+    pt.begin(4);
     int64_t half = g.lpts() / 2;
     VelArgs va = vs.va;
     if (g.slab)
@@ -451,6 +668,7 @@ class CufftEngine final : public Engine {
     else
       k_product<3><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nzl);
     ++own_launches;
+    pt.end();
     fwd(gr[0].p, dh[0].p);
   }
 
@@ -605,8 +823,14 @@ class CufftEngine final : public Engine {
   VelocityStore vs;
   DevBuf<double> cE, cE2, cZ, cA, cB, cG;
   DevBuf<char> work;
+  PhaseTimer pt;
   cufftHandle plan_fwd = 0, plan_inv = 0, plan_z = 0;
-  DevBuf<double2> T1, T2;  // slab transposes
+  DevBuf<double2> T1, T2, T3;  // slab transposes
+  cufftHandle plan_fwd_chunk = 0;
+  cudaStream_t s_comm = nullptr;
+  cudaEvent_t ev[16] = {nullptr};
+  bool slab_pipeline = false;
+  int n_chunks = 1;
   AxisTables axl;
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
   int64_t per_step_own = 0, per_step_lib = 0;
