@@ -1,0 +1,131 @@
+# PTFB200.jl — Julia-side glue for libptf_b200.so (the B200-native TracerAdvectionDiffusion hot path).
+#
+# Drop-in usage (same names as PassiveTracerFlows.TracerAdvectionDiffusion, new device type `B200`):
+#
+#     using PTFB200
+#     prob = PTFB200.Problem(B200(), TwoDAdvectingFlow(; u, v, steadyflow=true); nx, Lx, κ, dt, stepper="RK4")
+#     PTFB200.set_c!(prob, c0); stepforward!(prob, 25); PTFB200.updatevars!(prob); prob.vars.c
+#
+# UNTESTED HERE: this image has no Julia.  Every ccall below binds one symbol of include/ptf_b200.h; the Python
+# ctypes binding (passivetracerflows.jl_b200/_capi.py) is the tested twin of this file.
+module PTFB200
+
+export B200, Problem, set_c!, updatevars!, stepforward!, step_until!
+
+const LIB = get(ENV, "PTF_B200_LIB", "libptf_b200.so")
+
+struct B200                      # <: FourierFlows.Device in the real package (device seam, test/runtests.jl:12)
+  device::Int32
+end
+B200() = B200(-1)
+
+# mirror of `struct ptf_desc` (include/ptf_b200.h) — field order and types must match
+mutable struct PtfDesc
+  struct_size::UInt32; ndim::Int32
+  n::NTuple{3,Int64}; L::NTuple{3,Float64}
+  nbatch::Int32; stepper::Int32
+  kappa::NTuple{3,Float64}; kappa_h::Float64
+  n_kappa_h::Int32; dealias::Int32
+  aliased_fraction::Float64; dt::Float64
+  nyquist_sign::Int32; flow_kind::Int32; velocity_per_batch::Int32; engine::Int32
+  device::Int32; decomposition::Int32; nranks::Int32; rank::Int32
+  nccl_id::NTuple{128,UInt8}
+  filter_order::Float64; filter_inner_k::Float64; filter_outer_k::Float64; filter_tol::Float64
+  use_graph::Int32; reserved::NTuple{7,Int32}
+  PtfDesc() = new()
+end
+
+const STEPPERS = Dict("ForwardEuler"=>0, "RK4"=>1, "ETDRK4"=>2, "LSRK54"=>3, "AB3"=>4)
+stepper_id(s) = startswith(s, "Filtered") ? (STEPPERS[s[9:end]] | 16) : STEPPERS[s]
+
+function check(status::Int32, h=C_NULL)
+  status == 0 && return
+  msg = unsafe_string(ccall((:ptf_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
+  status == 1 ? throw(ArgumentError(msg)) : error("libptf_b200 [status $status]: $msg")   # cf. TAD.jl:234
+end
+
+mutable struct Clock; dt::Float64; t::Float64; step::Int; end
+mutable struct Vars; c::Array{Float64}; ch::Array{ComplexF64}; end
+
+mutable struct Prob
+  h::Ptr{Cvoid}; sol::Array{ComplexF64}; clock::Clock; vars::Vars
+  n::NTuple{3,Int}; L::NTuple{3,Float64}; ndim::Int
+  velocity                                   # keeps the @cfunction closure alive
+end
+
+gridpoints1(n, L) = range(-L/2, step=L/n, length=n)
+
+"Problem(dev::B200, flow; nx, Lx, ny, Ly, nz, Lz, κ, η, ι, dt, stepper) — TAD.jl:143-216"
+function Problem(dev::B200, flow; nx=128, Lx=2π, ny=nx, Ly=Lx, nz=nx, Lz=Lx, κ=0.1, η=κ, ι=κ, dt=0.01,
+                 stepper="RK4", κh=0.0, nκh=0, dealias=false)
+  fns  = hasproperty(flow, :w) ? (flow.u, flow.v, flow.w) : hasproperty(flow, :v) ? (flow.u, flow.v) : (flow.u,)
+  ndim = length(fns)
+  d = PtfDesc()
+  check(ccall((:ptf_desc_init, LIB), Int32, (Ref{PtfDesc},), d))
+  d.ndim = ndim; d.n = (nx, ny, nz); d.L = (Lx, Ly, Lz); d.kappa = (κ, η, ι); d.kappa_h = κh; d.n_kappa_h = nκh
+  d.dt = dt; d.stepper = stepper_id(stepper); d.dealias = dealias; d.device = dev.device
+  d.flow_kind = flow.steadyflow ? 0 : 1       # PTF_FLOW_STEADY / PTF_FLOW_CALLBACK
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:ptf_create, LIB), Int32, (Ref{PtfDesc}, Ref{Ptr{Cvoid}}), d, h))
+  dims  = (nx, ny, nz)[1:ndim]
+  sdims = (nx ÷ 2 + 1, dims[2:end]...)
+  x = gridpoints1(nx, Lx); y = gridpoints1(ny, Ly); z = gridpoints1(nz, Lz)
+  pts(i...) = ndim == 1 ? (x[i[1]],) : ndim == 2 ? (x[i[1]], y[i[2]]) : (x[i[1]], y[i[2]], z[i[3]])
+  keep = nothing
+  if flow.steadyflow                         # u.(x, y) evaluated once on gridpoints (TAD.jl:426-452)
+    for (a, f) in enumerate(fns)
+      U = [Float64(f(pts(Tuple(I)...)...)) for I in CartesianIndices(dims)]
+      GC.@preserve U check(ccall((:ptf_set_velocity, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64),
+                                 h[], a - 1, U, length(U)), h[])
+    end
+  else                                       # evaluated at clock.t once per step (TAD.jl:701,718,737)
+    npts = prod(dims)
+    function cb(user::Ptr{Cvoid}, t::Float64, pu::Ptr{Float64}, pv::Ptr{Float64}, pw::Ptr{Float64})::Cvoid
+      for (f, p) in zip(fns, (pu, pv, pw))
+        out = unsafe_wrap(Array, p, npts)
+        for (j, I) in enumerate(CartesianIndices(dims)); out[j] = f(pts(Tuple(I)...)..., t); end
+      end
+      nothing
+    end
+    keep = @cfunction($cb, Cvoid, (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}))
+    check(ccall((:ptf_set_velocity_callback, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), h[], keep, C_NULL), h[])
+  end
+  p = Prob(h[], zeros(ComplexF64, sdims), Clock(dt, 0.0, 0), Vars(zeros(dims), zeros(ComplexF64, sdims)),
+           (nx, ny, nz), (Lx, Ly, Lz), ndim, keep)
+  finalizer(q -> ccall((:ptf_destroy, LIB), Int32, (Ptr{Cvoid},), q.h), p)
+  return p
+end
+
+"set_c!(prob, c) — TAD.jl:844-872"
+function set_c!(p::Prob, c::Array{Float64})
+  GC.@preserve c check(ccall((:ptf_set_c, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), p.h, c, 0), p.h)
+  updatevars!(p)
+end
+
+"updatevars!(prob) — TAD.jl:815-837: refreshes the host mirrors prob.vars.c and prob.sol"
+function updatevars!(p::Prob)
+  check(ccall((:ptf_get_c, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), p.h, p.vars.c), p.h)
+  check(ccall((:ptf_get_sol, LIB), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}), p.h, p.sol), p.h)
+  p.vars.ch = p.sol
+  nothing
+end
+
+function sync_clock!(p::Prob)
+  t = Ref(0.0); s = Ref(Int64(0)); dt = Ref(0.0)
+  ccall((:ptf_get_clock, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}, Ref{Int64}, Ref{Float64}), p.h, t, s, dt)
+  p.clock.t, p.clock.step, p.clock.dt = t[], s[], dt[]
+end
+
+"stepforward!(prob[, nsteps]) — FourierFlows timesteppers.jl"
+function stepforward!(p::Prob, nsteps::Integer=1)
+  check(ccall((:ptf_step, LIB), Int32, (Ptr{Cvoid}, Int64), p.h, nsteps), p.h)
+  sync_clock!(p)
+end
+
+"step_until!(prob, stop_time) — FourierFlows (used at TAD.jl:238)"
+function step_until!(p::Prob, stop_time)
+  check(ccall((:ptf_step_until, LIB), Int32, (Ptr{Cvoid}, Float64), p.h, stop_time), p.h)
+  sync_clock!(p)
+end
+
+end # module
