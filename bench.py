@@ -376,6 +376,15 @@ def main():
         kernels[name] = {"ms": ms, "alg_bytes": alg_bytes}
     step_bytes = b_alg(2, args.stepper) * npts
     step_ms = dev_ms / (args.steps * NSUBS)
+    # measured DRAM traffic per launch (dram__bytes_read + dram__bytes_write) from the committed ncu --set full capture
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_fused_4096.json")))
+        for name, tag in (("ykernel", "k_fused_y"), ("xkernel", "k_fused_x")):
+            for pk in prof:
+                if tag in pk["kernel"] and name in kernels and nx == 4096:
+                    kernels[name]["traffic"] = pk["dram_traffic_bytes"]
+    except Exception:
+        pass
     for k in kernels.values():
         if k["alg_bytes"]:
             k["achieved_gbs"] = k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9
@@ -386,7 +395,8 @@ def main():
         if k["alg_bytes"]:
             ach = k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "ms_per_launch": k["ms"]}
+                    "traffic": k.get("traffic"), "peak_source": peak_src, "ms_per_launch": k["ms"],
+                    "alg_bytes_per_launch": k["alg_bytes"]}
     step_roof = {"b_alg_bytes_per_point_step": b_alg(2, args.stepper), "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
                  "peak": peak, "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak,
                  "ms_per_rk4_step": step_ms}

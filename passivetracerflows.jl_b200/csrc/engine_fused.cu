@@ -47,6 +47,8 @@ struct YArgs {
   const double* pf_r[4];      // real coefficient columns (ETDRK4), same
   int pf_ahead;               // > 0: also prefetch the P^x gather of the column `pf_ahead` CTAs ahead
   int ablate;                 // experiment bitmask (timing only): 1 = contiguous instead of gathered P^x
+  int stagger;                // first-wave de-phasing: odd CTAs of the first wave start `stagger` cycles late
+  int first_wave;             // number of CTAs resident at launch (2 per SM)
 };
 
 enum { FAM_RK4 = 0, FAM_ETD = 1, FAM_OTHER = 2 };
@@ -198,6 +200,14 @@ __global__ void __launch_bounds__(256, 2) k_fused_y(YArgs a) {
   constexpr int T = Cfg<NY>::T, F = 256 / T, PADN = Cfg<NY>::PADN;
   constexpr bool USE_TMEM = HAS_IN && FAM == FAM_RK4;   // N^ and s' parked in TMEM (see rk4_stage)
   extern __shared__ double2 smem[];
+  // De-phase the two CTAs resident on each SM: without this every first-wave CTA starts at the same instant and the
+  // whole chip alternates between memory phases (FP64 idle) and FFT phases (HBM idle) in lock-step.
+  if (a.stagger > 0 && (int)(blockIdx.x + gridDim.x * blockIdx.y) < a.first_wave && (blockIdx.x & 1)) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < a.stagger) {
+    }
+  }
+
   __shared__ uint32_t tslot;
   uint32_t tbase = 0, t_nh = 0, t_w = 0;
   if (USE_TMEM) {
@@ -345,6 +355,7 @@ struct XArgs {
   int pf_vel;    // 1: L2-prefetch this pair's u,v rows at CTA start
   int pf_ahead;  // > 0: L2-prefetch the A,B gather of the row pair `pf_ahead` CTAs ahead
   int ablate;    // experiment bitmask (timing only): 2 = no u,v loads
+  int stagger, first_wave;  // see YArgs
 };
 
 // ---- pieces of k_fused_x (free functions so that every register-array index is a compile-time constant) ----
@@ -438,6 +449,14 @@ __global__ void __launch_bounds__(256, 2) k_fused_x(XArgs a) {
   constexpr int T = Cfg<NX>::T, F = 256 / T, PADN = Cfg<NX>::PADN, H = NX / 2;
   constexpr int GB = 4;  // gather batch (k's per batch)
   extern __shared__ double2 smem[];
+  // De-phase the two CTAs resident on each SM: without this every first-wave CTA starts at the same instant and the
+  // whole chip alternates between memory phases (FP64 idle) and FFT phases (HBM idle) in lock-step.
+  if (a.stagger > 0 && (int)(blockIdx.x + gridDim.x * blockIdx.y) < a.first_wave && (blockIdx.x & 1)) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < a.stagger) {
+    }
+  }
+
   __shared__ uint32_t tslot;
   const uint32_t tbase = tmem::alloc_cta<256>(&tslot);
   const uint32_t t_in = tmem::warp_addr(tbase, 128);  // 64 columns: row-1 A,B   | 64 columns: u,v of the current row
@@ -809,6 +828,11 @@ class FusedEngine final : public Engine {
       tune_pf_ahead_x = env_int("PTF_PF_AHEAD_X", 0);
       g_smem_pad = (size_t)env_int("PTF_SMEM_PAD", 0);
       tune_ablate_x = env_int("PTF_ABLATE_X", 0);
+      // measured on B200 at 4096^2 (profiles/r01_fft_core_experiments.md): -2 % step time; only applied to launches
+      // of >= 4 waves (see run_x / yargs), where an 8-10 us head start is negligible
+      tune_stagger_x = env_int("PTF_STAGGER_X", 15000);
+      tune_stagger_y = env_int("PTF_STAGGER_Y", 20000);
+      PTF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx.device));
       tune_ablate_y = env_int("PTF_ABLATE_Y", 0);
     }
     PTF_DISPATCH_N(ny, prep_y<NN>());
@@ -951,6 +975,12 @@ class FusedEngine final : public Engine {
     }
     a.pf_ahead = tune_pf_ahead_y;
     a.ablate = tune_ablate_y;
+    a.first_wave = 2 * n_sm;
+    {
+      const int fy = 256 / (ny / 16);
+      const long ctas = (long)((nkr + fy - 1) / fy) * nb;
+      a.stagger = ctas >= 4L * a.first_wave ? tune_stagger_y : 0;
+    }
     return a;
   }
 
@@ -975,6 +1005,12 @@ class FusedEngine final : public Engine {
     a.pf_vel = tune_pf_vel;
     a.pf_ahead = tune_pf_ahead_x;
     a.ablate = tune_ablate_x;
+    a.first_wave = 2 * n_sm;
+    {
+      const int fx = 256 / (nx / 16);
+      const long ctas = (long)((ny / 2) / fx) * nb;
+      a.stagger = ctas >= 4L * a.first_wave ? tune_stagger_x : 0;
+    }
     int vmode = (vs.va.kind == PTF_FLOW_SEPARABLE) ? 2 : (vs.va.ushift ? 1 : 0);
     if (vmode != 2 && (!vs.va.arr[0] || !vs.va.arr[1]))
       throw Error(PTF_EINVAL, "velocity fields have not been set (ptf_set_velocity / callback)");
@@ -1128,7 +1164,7 @@ class FusedEngine final : public Engine {
   VelocityStore vs;
   cufftHandle plan_fwd = 0, plan_inv = 0;
   bool ab_valid = false;
-  int tune_ablate_x = 0, tune_ablate_y = 0;
+  int tune_ablate_x = 0, tune_ablate_y = 0, tune_stagger_x = 0, tune_stagger_y = 0, n_sm = 148;
   int tune_pf_state = 0, tune_pf_vel = 0, tune_pf_ahead_y = 0, tune_pf_ahead_x = 0;
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
   int64_t per_step_own = 0;
