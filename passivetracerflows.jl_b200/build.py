@@ -8,6 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libptf_b200.so")
 SOURCES = ["ptf_api.cu", "engine_cufft.cu", "engine_fused.cu"]
+FUSED_SIZES = [256, 512, 1024, 2048, 4096]   # fused_inst.cu is compiled once per transform length (in parallel)
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -43,14 +44,16 @@ def build(force=False, verbose=False, with_nccl=True):
         common += ["-DPTF_WITH_NCCL"]
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     procs = []
-    for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+    jobs = [(s, s.replace(".cu", ".o"), []) for s in SOURCES]
+    jobs += [("fused_inst.cu", f"fused_inst_{n}.o", [f"-DPTF_INST_N={n}"]) for n in FUSED_SIZES]
+    for s, oname, extra in jobs:
+        o = os.path.join(HERE, "build", oname)
         objs.append(o)
         src = os.path.join(CSRC, s)
         if (not force) and os.path.exists(o) and os.path.getmtime(o) > _newest(
                 [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [src]):
             continue
-        procs.append((s, subprocess.Popen(common + ["-c", src, "-o", o], stdout=subprocess.PIPE,
+        procs.append((oname, subprocess.Popen(common + extra + ["-c", src, "-o", o], stdout=subprocess.PIPE,
                                           stderr=subprocess.STDOUT, text=True)))
     for s, p in procs:
         out, _ = p.communicate()

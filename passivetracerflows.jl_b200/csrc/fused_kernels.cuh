@@ -1,0 +1,849 @@
+#pragma once
+// Kernels of the fused 2-D engine (included by engine_fused.cu and by fused_inst.cu, which is compiled once per
+// transform length so that the sizes build in parallel).
+//
+// Fused 2-D engine: the whole RK4/ETDRK4/... stage as TWO hand-written kernels, no cuFFT on the step path.
+//
+//   k_fused_y (one CTA sub-group per kr column, all y/l in registers+smem):
+//       gather P^x(y,kr) -> forward FFT_y -> N^(kr,l)                      (second half of rfft,  TAD.jl:766)
+//       stage combine in registers: addlinearterm! + substepsol!/update!   (FF timesteppers.jl), L/filter on the fly
+//       next stage state s' -> A = IFFT_y(s'/N), B = IFFT_y(i*l*s'/N)      (first half of the 2 irffts, TAD.jl:757-761)
+//   k_fused_x (one CTA sub-group per pair of y rows):
+//       gather A,B(kr,y) -> Z = i*kr*A + i*B (two-for-one Hermitian packing) -> inverse FFT_x -> gx + i*gy
+//       p = -u*gx - v*gy                                                    (TAD.jl:764)
+//       rows y,y+1 packed as p_y + i*p_{y+1} -> forward FFT_x -> split -> P^x(y,kr)   (first half of rfft)
+//
+// Data layout in HBM: spectral state (sol, sol_1, acc, ...) and A,B are stored TRANSPOSED, [b][kr][l|y]
+// (the column kernel's natural order); P^x is [b][y][kr] (the row kernel's natural order).  Every kernel WRITES
+// contiguously and READS the other kernel's layout with 16-byte strided gathers: measured on B200
+// (profiles/r01_microbench_strided_bw.txt) strided reads keep 75-95 % of copy bandwidth, strided partial-sector
+// writes only 25-47 %.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "fft_core.cuh"
+#include "ptf_pointwise.cuh"
+#include "ptf_velocity.cuh"
+#include "tmem_park.cuh"
+
+namespace ptf {
+
+namespace {
+
+using fft::Cfg;
+using fft::out_slot;
+using fft::pad_idx;
+using fft::Twiddles;
+
+struct YArgs {
+  const double2* Px;          // [b][y][kr]     nonlinear term, x-transformed (HAS_IN)
+  double2* A;                 // [b][kr][y]     IFFT_y(s')           (HAS_OUT)
+  double2* Bf;                // [b][kr][y]     IFFT_y(i*l*s')       (HAS_OUT)
+  const double2* next_state;  // [b][kr][l]     array holding s' after the combine (s0 for the prologue)
+  CombinePtrs P;
+  CombineArgs C;
+  AxisTables ax;
+  Twiddles tw;
+  int nkr;
+  double inv_n;               // 1/(nx*ny): normalisation of ldiv!(., rfftplan, .)
+  const double2* pf_c[4];     // complex state columns the combine will read: L2-prefetched at CTA start
+  const double* pf_r[4];      // real coefficient columns (ETDRK4), same
+  int pf_ahead;               // > 0: also prefetch the P^x gather of the column `pf_ahead` CTAs ahead
+  int ablate;                 // experiment bitmask (timing only): 1 = contiguous instead of gathered P^x
+  int stagger;                // first-wave de-phasing: odd CTAs of the first wave start `stagger` cycles late
+  int first_wave;             // number of CTAs resident at launch (2 per SM)
+};
+
+enum { FAM_RK4 = 0, FAM_ETD = 1, FAM_OTHER = 2 };
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// FourierFlows filter, out of line: sqrt/exp/pow would otherwise be inlined once per register element
+__device__ __noinline__ double filter_slow(double fx, double fy, double f_inner, double f_decay, double f_order,
+                                           double kx, double ky) {
+  double a = kx * fx, b = ky * fy;
+  double K = sqrt(a * a + b * b);
+  if (K < f_inner) return 1.0;
+  return exp(-f_decay * pow(K - f_inner, f_order));
+}
+
+// ---- RK4 family (FF RK4substeps!/RK4update!).  N^ (t_nh) and the new stage state s' (t_w) live in TMEM, so a
+// ---- batch of NB elements can have all 3*NB of its 16-byte state loads in flight at once (2 memory round trips
+// ---- per column instead of 4) and nothing accumulates in registers.
+template <int NY, int MODE>
+__device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_t t_w, size_t col, int t, double kx,
+                                          bool active, const double (&fl)[16]) {
+  constexpr int T = Cfg<NY>::T, NB = 8;
+  const double dt = a.C.dt;
+#pragma unroll
+  for (int e0 = 0; e0 < 16; e0 += NB) {
+    double2 ss[NB], s0[NB], ac[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const size_t i = col + t + T * (e0 + j);
+      s0[j] = __ldcg(a.P.s0 + i);
+      if (MODE != CM_RK4_S1) {
+        ss[j] = __ldcg(a.P.s1 + i);
+        ac[j] = __ldcg(a.P.acc + i);
+      }
+    }
+#pragma unroll
+    for (int j0 = 0; j0 < NB; j0 += 4) {
+      double2 nh[4];
+      tmem::ldn<4>(t_nh + 4 * (e0 + j0), nh);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = j0 + jj, e = e0 + j, l = t + T * e;
+        const size_t i = col + l;
+        const double ky = a.ax.ky[l];
+        const double L = lin_op(a.ax, kx, ky, 0.0);
+        const double2 Nh = nh[jj];
+        double2 next;
+        if (MODE == CM_RK4_S1) {
+          double2 k = cadd(Nh, cmul_r(s0[j], L));
+          next = cadd(s0[j], cmul_r(k, dt / 2));
+          if (active) {
+            __stcg(a.P.acc + i, cdiv_r(k, 6.0));
+            __stcg(a.P.s1 + i, next);
+          }
+        } else if (MODE == CM_RK4_S2 || MODE == CM_RK4_S3) {
+          double2 k = cadd(Nh, cmul_r(ss[j], L));
+          next = cadd(s0[j], cmul_r(k, MODE == CM_RK4_S2 ? dt / 2 : dt));
+          if (active) {
+            __stcg(a.P.acc + i, cadd(ac[j], cdiv_r(k, 3.0)));
+            __stcg(a.P.s1 + i, next);
+          }
+        } else {  // CM_RK4_S4
+          double2 k = cadd(Nh, cmul_r(ss[j], L));
+          double2 sum = cadd(ac[j], cdiv_r(k, 6.0));
+          next = cadd(s0[j], cmul_r(sum, dt));
+          if (a.C.filtered) next = cmul_r(next, fl[e]);
+          if (active) __stcg(a.P.s0 + i, next);
+        }
+        tmem::st1(t_w + 4 * e, make_double2(next.x * a.inv_n, next.y * a.inv_n));
+      }
+    }
+  }
+  tmem::wait_st();
+}
+
+// ---- ETDRK4 family (FF ETDRK4substeps!/ETDRK4update!)
+template <int NY, int MODE>
+__device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16], double2 (&w)[16], size_t col,
+                                          size_t ccol, int t, double kx, bool active, const double (&fl)[16]) {
+  constexpr int T = Cfg<NY>::T, NB = 4;
+#pragma unroll
+  for (int e0 = 0; e0 < 16; e0 += NB) {
+    double2 sa[NB], n1[NB], ac[NB];
+    double c0[NB], c1[NB], c2[NB], c3[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const size_t i = col + t + T * (e0 + j), ci = ccol + t + T * (e0 + j);
+      if (MODE == CM_ETD_S1 || MODE == CM_ETD_S2) {
+        sa[j] = __ldcg(a.P.s0 + i);
+        c0[j] = __ldcg(a.P.E2 + ci);
+        c1[j] = __ldcg(a.P.zeta + ci);
+      } else if (MODE == CM_ETD_S3) {
+        sa[j] = __ldcg(a.P.s1 + i);
+        n1[j] = __ldcg(a.P.n1 + i);
+        ac[j] = __ldcg(a.P.acc + i);
+        c0[j] = __ldcg(a.P.E2 + ci);
+        c1[j] = __ldcg(a.P.zeta + ci);
+      } else {
+        sa[j] = __ldcg(a.P.s0 + i);
+        n1[j] = __ldcg(a.P.n1 + i);
+        ac[j] = __ldcg(a.P.acc + i);
+        c0[j] = __ldcg(a.P.E + ci);
+        c1[j] = __ldcg(a.P.alpha + ci);
+        c2[j] = __ldcg(a.P.beta + ci);
+        c3[j] = __ldcg(a.P.gamma + ci);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int e = e0 + j, l = t + T * e;
+      const size_t i = col + l;
+      const double2 Nh = v[out_slot<NY>(e)];
+      double2 next;
+      if (MODE == CM_ETD_S1) {
+        next = cadd(cmul_r(sa[j], c0[j]), cmul_r(Nh, c1[j]));
+        if (active) {
+          __stcg(a.P.n1 + i, Nh);
+          __stcg(a.P.s1 + i, next);
+        }
+      } else if (MODE == CM_ETD_S2) {
+        next = cadd(cmul_r(sa[j], c0[j]), cmul_r(Nh, c1[j]));
+        if (active) {
+          __stcg(a.P.acc + i, Nh);
+          __stcg(a.P.s2 + i, next);
+        }
+      } else if (MODE == CM_ETD_S3) {
+        double2 tt = make_double2(2 * Nh.x - n1[j].x, 2 * Nh.y - n1[j].y);
+        next = cadd(cmul_r(sa[j], c0[j]), cmul_r(tt, c1[j]));
+        if (active) {
+          __stcg(a.P.acc + i, cadd(ac[j], Nh));
+          __stcg(a.P.s2 + i, next);
+        }
+      } else {
+        double2 r = cmul_r(sa[j], c0[j]);
+        r = cadd(r, cmul_r(n1[j], c1[j]));
+        r = cadd(r, cmul_r(ac[j], 2 * c2[j]));
+        r = cadd(r, cmul_r(Nh, c3[j]));
+        if (a.C.filtered) r = cmul_r(r, fl[e]);
+        next = r;
+        if (active) __stcg(a.P.s0 + i, next);
+      }
+      w[e] = make_double2(next.x * a.inv_n, next.y * a.inv_n);
+    }
+  }
+}
+
+// NT = threads per CTA (64, 128 or 256; >= T).  Small problems use small CTAs so that enough CTAs exist to fill the
+// 148 SMs; TMEM is allocated 128 columns per warp-quarter, i.e. 128 columns per CTA up to 4 warps, 256 for 8 warps.
+template <int NY, int FAM, bool HAS_IN, bool HAS_OUT, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
+  constexpr int T = Cfg<NY>::T, F = NT / T, PADN = Cfg<NY>::PADN;
+  constexpr int TCOLS = NT > 128 ? 256 : 128;
+  static_assert(NT >= T && NT % T == 0, "CTA must hold whole transforms");
+  constexpr bool USE_TMEM = HAS_IN && FAM == FAM_RK4;   // N^ and s' parked in TMEM (see rk4_stage)
+  extern __shared__ double2 smem[];
+  // De-phase the two CTAs resident on each SM: without this every first-wave CTA starts at the same instant and the
+  // whole chip alternates between memory phases (FP64 idle) and FFT phases (HBM idle) in lock-step.
+  if (a.stagger > 0 && (int)(blockIdx.x + gridDim.x * blockIdx.y) < a.first_wave && (blockIdx.x & 1)) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < a.stagger) {
+    }
+  }
+
+  __shared__ uint32_t tslot;
+  uint32_t tbase = 0, t_nh = 0, t_w = 0;
+  if (USE_TMEM) {
+    tbase = tmem::alloc_cta<TCOLS>(&tslot);
+    t_nh = tmem::warp_addr(tbase, 128);
+    t_w = t_nh + 64;
+  }
+  const int grp = threadIdx.x / T, t = threadIdx.x % T;
+  const int kr_raw = blockIdx.x * F + grp;
+  const bool active = kr_raw < a.nkr;
+  const int kr = active ? kr_raw : 0;
+  const int b = blockIdx.y;
+  double2* sm = smem + grp * PADN;
+  const size_t col = ((size_t)b * a.nkr + kr) * NY;  // this column in the transposed state arrays
+  const size_t ccol = (size_t)kr * NY;               // ... in the batch-shared coefficient arrays
+  const double kx = a.ax.kx[kr];
+  double2 w[16];
+  double fl[16];  // FourierFlows filter of this thread's 16 modes (final stage of Filtered* steppers only)
+  if (HAS_IN && FAM != FAM_OTHER && a.C.filtered && (a.C.mode == CM_RK4_S4 || a.C.mode == CM_ETD_S4)) {
+#pragma unroll 1
+    for (int e = 0; e < 16; ++e)
+      fl[e] = filter_slow(a.ax.fx, a.ax.fy, a.ax.f_inner, a.ax.f_decay, a.ax.f_order, kx, a.ax.ky[t + T * e]);
+  }
+
+  if (HAS_IN) {
+    double2 v[16];
+    const double2* P = a.Px + (size_t)b * NY * a.nkr + kr;
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      v[e] = __ldcg((a.ablate & 1) ? (a.Px + col + t + T * e) : (P + (size_t)(t + T * e) * a.nkr));  // L2-only: streamed once
+    // Pull the state columns the combine needs into L2 while the gather + forward FFT run (fire and forget).
+    if ((t & 7) == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (a.pf_c[q]) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) prefetch_l2(a.pf_c[q] + col + t + T * e);
+        }
+    }
+    if (FAM == FAM_ETD && (t & 15) == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (a.pf_r[q]) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) prefetch_l2(a.pf_r[q] + ccol + t + T * e);
+        }
+    }
+    fft::fft_cta<NY, -1>(v, sm, t, a.tw);
+    if (a.pf_ahead > 0) {  // next wave's gather: one 32-byte sector per (y, kr') pair
+      const int kr2 = kr_raw + a.pf_ahead * F;
+      if (kr2 < a.nkr) {
+        const double2* P2 = a.Px + (size_t)b * NY * a.nkr + kr2;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) prefetch_l2(P2 + (size_t)(t + T * e) * a.nkr);
+      }
+    }
+    if (FAM == FAM_RK4) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) tmem::st1(t_nh + 4 * e, v[out_slot<NY>(e)]);
+      tmem::wait_st();
+      switch (a.C.mode) {
+        case CM_RK4_S1: rk4_stage<NY, CM_RK4_S1>(a, t_nh, t_w, col, t, kx, active, fl); break;
+        case CM_RK4_S2: rk4_stage<NY, CM_RK4_S2>(a, t_nh, t_w, col, t, kx, active, fl); break;
+        case CM_RK4_S3: rk4_stage<NY, CM_RK4_S3>(a, t_nh, t_w, col, t, kx, active, fl); break;
+        default: rk4_stage<NY, CM_RK4_S4>(a, t_nh, t_w, col, t, kx, active, fl); break;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double2 r4[4];
+        tmem::ldn<4>(t_w + 16 * q, r4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[4 * q + j] = r4[j];
+      }
+    } else if (FAM == FAM_ETD) {
+      switch (a.C.mode) {
+        case CM_ETD_S1: etd_stage<NY, CM_ETD_S1>(a, v, w, col, ccol, t, kx, active, fl); break;
+        case CM_ETD_S2: etd_stage<NY, CM_ETD_S2>(a, v, w, col, ccol, t, kx, active, fl); break;
+        case CM_ETD_S3: etd_stage<NY, CM_ETD_S3>(a, v, w, col, ccol, t, kx, active, fl); break;
+        default: etd_stage<NY, CM_ETD_S4>(a, v, w, col, ccol, t, kx, active, fl); break;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int l = t + T * e;
+        double2 nx = make_double2(0.0, 0.0);
+        if (active)
+          nx = combine_at<CMASK_OTHER>(a.P, a.C, a.ax, col + l, ccol + l, kx, a.ax.ky[l], 0.0, v[out_slot<NY>(e)]);
+        w[e] = make_double2(nx.x * a.inv_n, nx.y * a.inv_n);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      double2 s = __ldcg(a.next_state + col + t + T * e);
+      w[e] = make_double2(s.x * a.inv_n, s.y * a.inv_n);
+    }
+  }
+  if (!HAS_OUT) {
+    if (USE_TMEM) tmem::free_cta<TCOLS>(tbase);
+    return;
+  }
+
+  fft::fft_cta<NY, +1>(w, sm, t, a.tw);
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) __stcg(a.A + col + t + T * e, w[out_slot<NY>(e)]);
+  }
+  // y-derivative: i*l*s'
+  if (USE_TMEM) {  // s'/N is still parked in TMEM: no second trip to global memory
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double2 r4[4];
+      tmem::ldn<4>(t_w + 16 * q, r4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double ky = a.ax.ky[t + T * (4 * q + j)];
+        w[4 * q + j] = make_double2(-ky * r4[j].y, ky * r4[j].x);
+      }
+    }
+  } else {         // s' re-read from the array this thread just wrote: L2 hit, no DRAM traffic
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int l = t + T * e;
+      double2 s = __ldcg(a.next_state + col + l);
+      double ky = a.ax.ky[l] * a.inv_n;
+      w[e] = make_double2(-ky * s.y, ky * s.x);
+    }
+  }
+  fft::fft_cta<NY, +1>(w, sm, t, a.tw);
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) __stcg(a.Bf + col + t + T * e, w[out_slot<NY>(e)]);
+  }
+  if (USE_TMEM) tmem::free_cta<TCOLS>(tbase);
+}
+
+struct XArgs {
+  const double2* A;   // [b][kr][y]
+  const double2* Bf;  // [b][kr][y]
+  double2* Px;        // [b][y][kr]
+  VelArgs va;
+  AxisTables ax;
+  Twiddles tw;
+  int nkr, ny;
+  int pf_vel;    // 1: L2-prefetch this pair's u,v rows at CTA start
+  int pf_ahead;  // > 0: L2-prefetch the A,B gather of the row pair `pf_ahead` CTAs ahead
+  int ablate;    // experiment bitmask (timing only): 2 = no u,v loads
+  int stagger, first_wave;  // see YArgs
+};
+
+// ---- pieces of k_fused_x (free functions so that every register-array index is a compile-time constant) ----
+// Z = X + iY with X = i*kr*A (-> gx), Y = B (-> gy) for the lower half k = t + T*e < NX/2; the mirrored bin NX-k
+// gets conj(X) + i*conj(Y) and is handed to its owner through shared memory.
+template <int NX>
+__device__ __forceinline__ void x_lower(double2& ve, int e, int t, double2 Av, double2 Bv,
+                                        const double* __restrict__ kxt, double2* __restrict__ sm) {
+  constexpr int T = Cfg<NX>::T;
+  const int k = t + T * e;
+  const double kx = kxt[k];
+  const double Xx = -kx * Av.y, Xy = kx * Av.x;
+  if (e == 0 && t == 0) {
+    ve = make_double2(Xx, Bv.x);  // c2r ignores the imaginary part of the DC bin
+  } else {
+    ve = make_double2(Xx - Bv.y, Xy + Bv.x);
+    sm[pad_idx(NX - k)] = make_double2(Xx + Bv.y, Bv.x - Xy);
+  }
+}
+// bin k = NX/2: real part only (c2r semantics)
+template <int NX>
+__device__ __forceinline__ void x_nyquist(int t, const double2* Ab, const double2* Bb, int ny, int q,
+                                          const double* __restrict__ kxt, double2* __restrict__ sm) {
+  constexpr int H = NX / 2;
+  if (t == 0) {
+    double2 Av = __ldcg(Ab + (size_t)H * ny + q);
+    double2 Bv = __ldcg(Bb + (size_t)H * ny + q);
+    sm[pad_idx(H)] = make_double2(-kxt[H] * Av.y, Bv.x);
+  }
+}
+// velocity row -> TMEM (its latency hides behind the inverse transform that follows)
+template <int NX, int VMODE>
+__device__ __forceinline__ void x_request_uv(const XArgs& a, size_t voff, int q, int t, uint32_t t_uv) {
+  constexpr int T = Cfg<NX>::T;
+  constexpr int UB = 16;  // velocity request batch
+  if (VMODE != 2) {
+#pragma unroll
+    for (int h = 0; h < 16 / UB; ++h) {
+      double2 uv[UB];
+#pragma unroll
+      for (int j = 0; j < UB; ++j) {
+        const size_t i = voff + (size_t)q * NX + t + T * (UB * h + j);
+        if (a.ablate & 2) uv[j] = make_double2(0.5, 0.25);
+        else uv[j] = make_double2(tmem::ldg64(a.va.arr[0] + i), tmem::ldg64(a.va.arr[1] + i));
+      }
+#pragma unroll
+      for (int j = 0; j < UB; ++j) tmem::st1(t_uv + 4 * (UB * h + j), uv[j]);
+    }
+  }
+  tmem::wait_st();
+}
+// physical space: v = gx + i*gy at x = t + T*e;  p = -u*gx - v*gy  (TAD.jl:764)
+template <int NX, int VMODE, int Q>
+__device__ __forceinline__ void x_product(const XArgs& a, const double2 (&v)[16], double2 (&w)[16],
+                                          double* __restrict__ ps, int t, uint32_t t_uv, int b, int pair) {
+  constexpr int T = Cfg<NX>::T;
+  const int row = 2 * pair + Q;
+  constexpr int PB = 4;  // velocity fetch batch
+#pragma unroll
+  for (int c = 0; c < 16 / PB; ++c) {
+    double2 uv[PB];
+    if (VMODE != 2) tmem::ldn<PB>(t_uv + 4 * PB * c, uv);
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int e = PB * c + j, x = t + T * e;
+      const double2 g = v[out_slot<NX>(e)];
+      double u, vv;
+      if (VMODE == 2) {
+        u = sep_eval(a.va.sep[0], x, row, 0, NX, a.ny, 1, 2);
+        vv = sep_eval(a.va.sep[1], x, row, 0, NX, a.ny, 1, 2);
+      } else {
+        u = uv[j].x;
+        vv = uv[j].y;
+        if (a.va.ushift) u += a.va.ushift[b * a.ny + row];  // layered flows: u + U(y, layer)  (TAD.jl:795)
+      }
+      const double p = -u * g.x - vv * g.y;
+      if (Q == 0) ps[x] = p;                     // row 0: parked in shared memory while row 1 runs
+      else w[e] = make_double2(ps[x], p);        // row 1: packed with row 0 as p_y + i*p_{y+1} for the forward FFT
+    }
+  }
+}
+
+// VMODE 0: velocity arrays; 1: arrays + layered shift U(y,b); 2: separable tables (zero HBM bytes)
+//
+// Memory choreography (what the ablation study in profiles/ asked for): A[k][y], A[k][y+1] are 32 contiguous bytes,
+// so ONE 256-bit load per k fetches both rows of the pair (half the L1 tag look-ups of two 16-byte gathers, one
+// memory round trip instead of two); row 1's share is parked in TMEM until row 0 is done.  The velocity rows are
+// requested before each inverse transform and parked in TMEM as well, so their latency hides behind the FFT.
+template <int NX, int VMODE, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
+  constexpr int T = Cfg<NX>::T, F = NT / T, PADN = Cfg<NX>::PADN, H = NX / 2;
+  constexpr int TCOLS = NT > 128 ? 256 : 128;
+  static_assert(NT >= T && NT % T == 0, "CTA must hold whole transforms");
+  constexpr int GB = 4;  // gather batch (k's per batch)
+  extern __shared__ double2 smem[];
+  // De-phase the two CTAs resident on each SM: without this every first-wave CTA starts at the same instant and the
+  // whole chip alternates between memory phases (FP64 idle) and FFT phases (HBM idle) in lock-step.
+  if (a.stagger > 0 && (int)(blockIdx.x + gridDim.x * blockIdx.y) < a.first_wave && (blockIdx.x & 1)) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < a.stagger) {
+    }
+  }
+
+  __shared__ uint32_t tslot;
+  const uint32_t tbase = tmem::alloc_cta<TCOLS>(&tslot);
+  const uint32_t t_in = tmem::warp_addr(tbase, 128);  // 64 columns: row-1 A,B   | 64 columns: u,v of the current row
+  const uint32_t t_uv = t_in + 64;
+  const int grp = threadIdx.x / T, t = threadIdx.x % T;
+  const int pair = blockIdx.x * F + grp;
+  const int b = blockIdx.y;
+  const int ny = a.ny;
+  double2* sm = smem + grp * PADN;
+  double* ps = reinterpret_cast<double*>(smem + F * PADN) + grp * NX;  // row-0 product, parked while row 1 runs
+  const double2* Ab = a.A + (size_t)b * a.nkr * ny + 2 * pair;
+  const double2* Bb = a.Bf + (size_t)b * a.nkr * ny + 2 * pair;
+  const size_t voff = (size_t)b * a.va.member_stride + (size_t)(2 * pair) * NX;
+  double2 v[16];
+
+  // row 0's inputs, and the parking of row 1's
+#pragma unroll
+  for (int h = 0; h < 8 / GB; ++h) {  // batches of GB k's: 2*GB 256-bit requests in flight per thread
+    double2 A0[GB], A1[GB], B0[GB], B1[GB];
+#pragma unroll
+    for (int j = 0; j < GB; ++j) {
+      const size_t gi = (size_t)(t + T * (GB * h + j)) * ny;
+      tmem::ldg256(Ab + gi, A0[j], A1[j]);
+      tmem::ldg256(Bb + gi, B0[j], B1[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < GB; ++j) {
+      tmem::st1(t_in + 8 * (GB * h + j), A1[j]);
+      tmem::st1(t_in + 8 * (GB * h + j) + 4, B1[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < GB; ++j) x_lower<NX>(v[GB * h + j], GB * h + j, t, A0[j], B0[j], a.ax.kx, sm);
+  }
+#pragma unroll 1
+  for (int q = 0; q < 2; ++q) {  // deliberately NOT unrolled: one copy of the inverse transform keeps register
+                                 // pressure (and the instruction footprint) down
+    if (q == 1) {
+      __syncthreads();           // exchange buffer free (row 0's transform readers are done)
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        double2 AB[4];  // (A1, B1) of k-slots 2h, 2h+1
+        tmem::ldn<4>(t_in + 16 * h, AB);
+        x_lower<NX>(v[2 * h], 2 * h, t, AB[0], AB[1], a.ax.kx, sm);
+        x_lower<NX>(v[2 * h + 1], 2 * h + 1, t, AB[2], AB[3], a.ax.kx, sm);
+      }
+    }
+    x_nyquist<NX>(t, Ab, Bb, ny, q, a.ax.kx, sm);
+    x_request_uv<NX, VMODE>(a, voff, q, t, t_uv);  // includes tcgen05.wait::st for the parked inputs as well
+    __syncthreads();
+#pragma unroll
+    for (int e = 8; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
+    fft::fft_cta<NX, +1>(v, sm, t, a.tw);
+    if (q == 0) x_product<NX, VMODE, 0>(a, v, v, ps, t, t_uv, b, pair);
+  }
+  double2 w[16];
+  x_product<NX, VMODE, 1>(a, v, w, ps, t, t_uv, b, pair);
+
+  // ---------------- forward transform of the row pair packed as p_y + i*p_{y+1} ----------------
+  fft::fft_cta<NX, -1>(w, sm, t, a.tw);
+  __syncthreads();
+#pragma unroll
+  for (int e = 8; e < 16; ++e) sm[pad_idx(t + T * e)] = w[out_slot<NX>(e)];
+  __syncthreads();
+  double2* P0 = a.Px + ((size_t)b * ny + 2 * pair) * a.nkr;
+  double2* P1 = P0 + a.nkr;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = t + T * e;
+    double2 W = w[out_slot<NX>(e)];
+    double2 Wm = (e == 0 && t == 0) ? W : sm[pad_idx(NX - k)];
+    __stcg(P0 + k, make_double2(0.5 * (W.x + Wm.x), 0.5 * (W.y - Wm.y)));
+    __stcg(P1 + k, make_double2(0.5 * (W.y + Wm.y), 0.5 * (Wm.x - W.x)));
+  }
+  if (t == 0) {
+    double2 W = w[out_slot<NX>(8)];  // index 8*T = NX/2
+    P0[H] = make_double2(W.x, 0.0);
+    P1[H] = make_double2(W.y, 0.0);
+  }
+  tmem::free_cta<TCOLS>(tbase);
+}
+
+// out[b][c][r] = scale * in[b][r][c]   (layout changes at the set/get boundary only — not on the step path)
+__global__ void __launch_bounds__(256) k_transpose(const double2* __restrict__ in, double2* __restrict__ out, int R,
+                                                   int Cc, double scale) {
+  __shared__ double2 tile[32][33];
+  const int b = blockIdx.z;
+  const double2* I = in + (size_t)b * R * Cc;
+  double2* O = out + (size_t)b * R * Cc;
+  int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[j][threadIdx.x] = I[(size_t)r * Cc + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) {
+      double2 v = tile[threadIdx.x][j];
+      O[(size_t)c * R + r] = make_double2(v.x * scale, v.y * scale);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_replicate_f(double* __restrict__ c, int64_t npts, int64_t B) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = c[i];
+    for (int64_t b = 1; b < B; ++b) c[b * npts + i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_diag_t(const double2* __restrict__ s, int64_t nkr, int64_t ny, int64_t B,
+                                                int64_t nx, double* out) {
+  __shared__ double ssum[256];
+  __shared__ double smax[256];
+  int64_t n = nkr * ny * B;
+  double acc = 0, mx = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t ix = (i / ny) % nkr;
+    double2 v = s[i];
+    double a2 = v.x * v.x + v.y * v.y;
+    acc += ((ix == 0 || ix == nx / 2) ? 1.0 : 2.0) * a2;
+    mx = fmax(mx, a2);
+  }
+  ssum[threadIdx.x] = acc;
+  smax[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      ssum[threadIdx.x] += ssum[threadIdx.x + o];
+      smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    atomicAdd(&out[0], ssum[0]);
+    atomicMax(reinterpret_cast<unsigned long long*>(&out[1]), (unsigned long long)__double_as_longlong(smax[0]));
+  }
+}
+
+// ---- stand-alone transform test kernel (ptf_selftest_fft): `count` independent length-N transforms ----
+// experiment: compute-only rate of the transform (REP transforms per load/store)
+template <int N>
+__global__ void __launch_bounds__(256, 2) k_fft_rate_test(const double2* __restrict__ in, double2* __restrict__ out,
+                                                          int count, Twiddles tw, int rep) {
+  constexpr int T = Cfg<N>::T, F = 256 / T, PADN = Cfg<N>::PADN;
+  extern __shared__ double2 smem[];
+  const int grp = threadIdx.x / T, t = threadIdx.x % T;
+  const int id = blockIdx.x * F + grp;
+  const size_t base = (size_t)id * N;
+  double2 v[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = in[base + t + T * e];
+#pragma unroll 1
+  for (int r = 0; r < rep; ++r) {
+    fft::fft_cta<N, -1>(v, smem + grp * PADN, t, tw);
+    double2 w[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) w[e] = v[out_slot<N>(e)];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = make_double2(w[e].x * 0.015625, w[e].y * 0.015625);
+  }
+#pragma unroll
+  for (int e = 0; e < 16; ++e) out[base + t + T * e] = v[e];
+}
+
+template <int N, int DIR>
+__global__ void __launch_bounds__(256, 2) k_fft_test(const double2* __restrict__ in, double2* __restrict__ out,
+                                                     int count, Twiddles tw) {
+  constexpr int T = Cfg<N>::T, F = 256 / T, PADN = Cfg<N>::PADN;
+  extern __shared__ double2 smem[];
+  const int grp = threadIdx.x / T, t = threadIdx.x % T;
+  const int id = blockIdx.x * F + grp;
+  const bool active = id < count;
+  const size_t base = (size_t)(active ? id : 0) * N;
+  double2 v[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = in[base + t + T * e];
+  fft::fft_cta<N, DIR>(v, smem + grp * PADN, t, tw);
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) out[base + t + T * e] = v[out_slot<N>(e)];
+  }
+}
+
+// experiment: same transform, but the input is read as column `id` of a row-major [N][count] matrix (16-byte gathers,
+// the access pattern of k_fused_y's P^x read / k_fused_x's A,B read); PAIR = 1 reads 32-byte lane pairs
+template <int N, int PAIR>
+__global__ void __launch_bounds__(256, 2) k_fft_gather_test(const double2* __restrict__ in, double2* __restrict__ out,
+                                                            int count, Twiddles tw) {
+  constexpr int T = Cfg<N>::T, F = 256 / T, PADN = Cfg<N>::PADN;
+  extern __shared__ double2 smem[];
+  const int grp = threadIdx.x / T, t = threadIdx.x % T;
+  const int id = blockIdx.x * F + grp;
+  const size_t base = (size_t)id * N;
+  double2 v[16];
+  if (PAIR == 0) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = __ldcg(in + (size_t)(t + T * e) * count + id);
+  } else {
+    // lanes (2j, 2j+1) read the two halves of one 32-byte sector: element index t>>1 + ..., column 2*id' + (t&1)
+    const int tt = t >> 1, c = t & 1;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = __ldcg(in + (size_t)(tt + (T / 2) * e) * count + 2 * (id / 2) + c);
+  }
+  fft::fft_cta<N, -1>(v, smem + grp * PADN, t, tw);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) __stcg(out + base + t + T * e, v[out_slot<N>(e)]);
+}
+
+// experiment / unit test of the pairing machinery: columns (2j, 2j+1) of a row-major [N][count] matrix are gathered
+// with 256-bit loads, the odd column is parked in TMEM while the even one is transformed, and the two results are
+// written back as 32-byte pairs (out[N][count], transform along axis 0).
+template <int N>
+__global__ void __launch_bounds__(256, 2) k_fft_pair_test(const double2* __restrict__ in, double2* __restrict__ out,
+                                                          int count, Twiddles tw) {
+  constexpr int T = Cfg<N>::T, F = 256 / T, PADN = Cfg<N>::PADN;
+  extern __shared__ double2 smem[];
+  __shared__ uint32_t tslot;
+  const uint32_t tbase = tmem::alloc_cta<256>(&tslot);
+  const uint32_t ta = tmem::warp_addr(tbase, 128);
+  const int grp = threadIdx.x / T, t = threadIdx.x % T;
+  const int pair = blockIdx.x * F + grp;
+  const bool active = 2 * pair < count;
+  const size_t c0 = 2 * (size_t)(active ? pair : 0);
+  double2 v[16], w[16];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {  // two batches of 8 pairs: 64 registers in flight, odd column parked at once
+    double2 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tmem::ldg256(in + (size_t)(t + T * (8 * h + j)) * count + c0, v[8 * h + j], o[j]);
+    tmem::st4(ta + 32 * h, o[0], o[1], o[2], o[3]);
+    tmem::st4(ta + 32 * h + 16, o[4], o[5], o[6], o[7]);
+  }
+  tmem::wait_st();
+  fft::fft_cta<N, -1>(v, smem + grp * PADN, t, tw);
+  tmem::park16(ta + 64, v, [](int i) { return out_slot<N>(i); });   // result of column 0, natural order
+  tmem::fetch16(ta, w);
+  fft::fft_cta<N, -1>(w, smem + grp * PADN, t, tw);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {  // fetch 4 parked results at a time: never more than 16 extra registers live
+    double2 a0, a1, a2, a3;
+    tmem::ld4(ta + 64 + 16 * q, a0, a1, a2, a3);
+    if (active) {
+      tmem::stg256(out + (size_t)(t + T * (4 * q + 0)) * count + c0, a0, w[out_slot<N>(4 * q + 0)]);
+      tmem::stg256(out + (size_t)(t + T * (4 * q + 1)) * count + c0, a1, w[out_slot<N>(4 * q + 1)]);
+      tmem::stg256(out + (size_t)(t + T * (4 * q + 2)) * count + c0, a2, w[out_slot<N>(4 * q + 2)]);
+      tmem::stg256(out + (size_t)(t + T * (4 * q + 3)) * count + c0, a3, w[out_slot<N>(4 * q + 3)]);
+    }
+  }
+  tmem::free_cta<256>(tbase);
+}
+
+bool is_fused_size(int64_t n) { return n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096; }
+
+// twiddle tables of one length, forward sign, rounded from long double
+struct TwiddleSet {
+  DevBuf<double2> tw2, tw3;
+  Twiddles dev() const { return Twiddles{tw2.p, tw3.p}; }
+  void build(int N, int64_t* tally) {
+    std::vector<double2> h2(4 * 16), h3(4 * 256);
+    const long double PI2 = 6.283185307179586476925286766559005768L;
+    for (int m = 0; m < 4; ++m)
+      for (int k = 0; k < 16; ++k) {
+        long double ang = -PI2 * (long double)((k << m) % 256) / 256.0L;
+        h2[m * 16 + k] = make_double2((double)cosl(ang), (double)sinl(ang));
+      }
+    for (int m = 0; m < 4; ++m)
+      for (int k = 0; k < 256; ++k) {
+        long double ang = -PI2 * (long double)(((long)k << m) % N) / (long double)N;
+        h3[m * 256 + k] = make_double2((double)cosl(ang), (double)sinl(ang));
+      }
+    tw2.alloc(h2.size(), tally);
+    tw3.alloc(h3.size(), tally);
+    PTF_CUDA(cudaMemcpy(tw2.p, h2.data(), h2.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    PTF_CUDA(cudaMemcpy(tw3.p, h3.data(), h3.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  }
+};
+
+// experiment knob (PTF_SMEM_PAD): extra dynamic smem to lower occupancy
+inline size_t smem_pad_knob() {
+  static const size_t v = [] {
+    const char* e = std::getenv("PTF_SMEM_PAD");
+    return e ? (size_t)std::atoi(e) : (size_t)0;
+  }();
+  return v;
+}
+#define g_smem_pad (smem_pad_knob())
+template <int N, int NT = 256>
+constexpr size_t y_smem() { return (size_t)(NT / Cfg<N>::T) * Cfg<N>::PADN * sizeof(double2); }
+template <int N, int NT = 256>
+constexpr size_t x_smem() { return y_smem<N, NT>() + (size_t)(NT / Cfg<N>::T) * N * sizeof(double); }
+
+template <class K>
+void allow_smem(K kernel, size_t bytes) {
+  PTF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+// CTA size for a launch of `items` transforms-groups: the largest NT in {256,128,64} (>= T) that still yields at
+// least 2 CTAs per SM, else the smallest allowed.
+template <int N>
+int pick_nt(long items, int n_sm) {
+  constexpr int T = Cfg<N>::T;
+  for (int nt : {256, 128, 64}) {
+    if (nt < T) break;
+    long ctas = (items + nt / T - 1) / (nt / T);
+    if (ctas >= 2L * n_sm || nt == 64 || nt / 2 < T) return nt;
+  }
+  return T > 64 ? T : 64;
+}
+
+template <int NY, int NT>
+void prep_y_nt() {  // opt in to > 48 KB dynamic shared memory (per device, so done at engine construction)
+  if constexpr (NT >= Cfg<NY>::T) {
+    allow_smem(k_fused_y<NY, FAM_RK4, false, true, NT>, y_smem<NY, NT>() + g_smem_pad);
+    allow_smem(k_fused_y<NY, FAM_RK4, true, true, NT>, y_smem<NY, NT>() + g_smem_pad);
+    allow_smem(k_fused_y<NY, FAM_ETD, true, true, NT>, y_smem<NY, NT>() + g_smem_pad);
+    allow_smem(k_fused_y<NY, FAM_OTHER, true, true, NT>, y_smem<NY, NT>() + g_smem_pad);
+  }
+}
+template <int NY>
+void prep_y() {
+  prep_y_nt<NY, 256>();
+  prep_y_nt<NY, 128>();
+  prep_y_nt<NY, 64>();
+}
+template <int NX, int NT>
+void prep_x_nt() {
+  if constexpr (NT >= Cfg<NX>::T) {
+    allow_smem(k_fused_x<NX, 0, NT>, x_smem<NX, NT>() + g_smem_pad);
+    allow_smem(k_fused_x<NX, 2, NT>, x_smem<NX, NT>() + g_smem_pad);
+  }
+}
+template <int NX>
+void prep_x() {
+  prep_x_nt<NX, 256>();
+  prep_x_nt<NX, 128>();
+  prep_x_nt<NX, 64>();
+}
+
+template <int NY, int NT>
+void launch_y_nt(bool has_in, int fam, const YArgs& a, int nb, cudaStream_t st) {
+  if constexpr (NT >= Cfg<NY>::T) {
+    constexpr int F = NT / Cfg<NY>::T;
+    dim3 grid((a.nkr + F - 1) / F, nb, 1);
+    size_t sm = y_smem<NY, NT>() + g_smem_pad;
+    if (!has_in) k_fused_y<NY, FAM_RK4, false, true, NT><<<grid, NT, sm, st>>>(a);
+    else if (fam == FAM_RK4) k_fused_y<NY, FAM_RK4, true, true, NT><<<grid, NT, sm, st>>>(a);
+    else if (fam == FAM_ETD) k_fused_y<NY, FAM_ETD, true, true, NT><<<grid, NT, sm, st>>>(a);
+    else k_fused_y<NY, FAM_OTHER, true, true, NT><<<grid, NT, sm, st>>>(a);
+  }
+}
+template <int NY>
+void launch_y(bool has_in, int fam, const YArgs& a, int nb, cudaStream_t st, int n_sm) {
+  int nt = pick_nt<NY>((long)a.nkr * nb, n_sm);
+  if (nt == 256) launch_y_nt<NY, 256>(has_in, fam, a, nb, st);
+  else if (nt == 128) launch_y_nt<NY, 128>(has_in, fam, a, nb, st);
+  else launch_y_nt<NY, 64>(has_in, fam, a, nb, st);
+}
+
+template <int NX, int NT>
+void launch_x_nt(int vmode, const XArgs& a, int nb, cudaStream_t st) {
+  if constexpr (NT >= Cfg<NX>::T) {
+    constexpr int F = NT / Cfg<NX>::T;
+    dim3 grid((a.ny / 2) / F, nb, 1);
+    size_t sm = x_smem<NX, NT>() + g_smem_pad;
+    if (vmode == 2) k_fused_x<NX, 2, NT><<<grid, NT, sm, st>>>(a);
+    else k_fused_x<NX, 0, NT><<<grid, NT, sm, st>>>(a);
+  }
+}
+template <int NX>
+void launch_x(int vmode, const XArgs& a, int nb, cudaStream_t st, int n_sm) {
+  int nt = pick_nt<NX>((long)(a.ny / 2) * nb, n_sm);
+  if (nt == 256) launch_x_nt<NX, 256>(vmode, a, nb, st);
+  else if (nt == 128) launch_x_nt<NX, 128>(vmode, a, nb, st);
+  else launch_x_nt<NX, 64>(vmode, a, nb, st);
+}
+
+
+}  // namespace
+}  // namespace ptf
