@@ -222,3 +222,51 @@ def test_fused_4096_one_step_against_oracle():
     g.stepforward(2)
     e = rel_l2(o.updatevars(), g.updatevars())
     assert e <= 2 * TOL_STEP, f"4096^2 after 2 steps: {e:.3e}"
+
+
+# ------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE's full size (4096^2), where the oracle is too slow for long runs
+# ------------------------------------------------------------------------------------------
+def _full_size_problem(stepper="RK4", engine="auto"):
+    P = _P()
+    nx = 4096
+    dt = 0.5 * 2.785 / (0.1 * 2 * (nx / 2) ** 2)
+    flow = P.TwoDAdvectingFlow(u=lambda x, y: 0.2 * np.cos(x) * np.sin(y), v=lambda x, y: -0.2 * np.sin(x) * np.cos(y))
+    prob = P.Problem(P.B200(engine=engine), flow, nx=nx, kappa=0.1, dt=dt, stepper=stepper)
+    x = prob.grid.x
+    c0 = 0.5 * np.exp(-((x[None, :] - 0.4 * np.pi) ** 2 + x[:, None] ** 2) / (2 * 0.15 ** 2))
+    return prob, c0
+
+
+def test_full_size_linearity_and_mean_conservation():
+    # the step is linear in c: step(a*c1 + b*c2) == a*step(c1) + b*step(c2); an incompressible flow conserves the mean
+    prob, c1 = _full_size_problem()
+    assert prob.engine == "fused"
+    c2 = np.roll(c1, (700, -900), axis=(0, 1)) * 0.7
+    outs = []
+    for c in (c1, c2, 2.0 * c1 - 3.0 * c2):
+        prob.set_c(c)
+        m0 = prob.diagnostics()["mean_c"]
+        prob.stepforward(5)
+        d = prob.diagnostics()
+        assert abs(d["mean_c"] - m0) <= 1e-13 * max(1.0, abs(m0)), "mean not conserved"
+        outs.append(prob.updatevars().copy())
+    assert rel_l2(2.0 * outs[0] - 3.0 * outs[1], outs[2]) <= 1e-13
+
+
+def test_full_size_engines_agree_and_variance_decays():
+    # fused and cuFFT engines are independent implementations: they must agree at 4096^2 over 20 steps, and the
+    # tracer variance must decay monotonically (advection by an incompressible flow + diffusion)
+    pf, c0 = _full_size_problem(engine="fused")
+    pc, _ = _full_size_problem(engine="cufft")
+    pf.set_c(c0)
+    pc.set_c(c0)
+    last = pf.diagnostics()["variance_c"]
+    for _ in range(4):
+        pf.stepforward(5)
+        pc.stepforward(5)
+        v = pf.diagnostics()["variance_c"]
+        assert v < last
+        last = v
+    assert rel_l2(pc.updatevars(), pf.updatevars()) <= 20 * TOL_STEP
+    assert abs(pc.diagnostics()["variance_c"] - last) <= 1e-12 * last
