@@ -254,6 +254,15 @@ void run_velocity_providers(ptf_handle* h) {
 
 void do_steps(ptf_handle* h, int64_t nsteps) {
   Context& c = h->ctx;
+  // no per-step host input (steady arrays, or a separable flow without a coefficient callback): the engine may run
+  // the whole call in one launch
+  const bool per_step_input = c.d.flow_kind == PTF_FLOW_CALLBACK ||
+                              (c.d.flow_kind == PTF_FLOW_SEPARABLE && h->coeff_fn != nullptr);
+  if (!per_step_input && nsteps > 0 && h->engine->step_many(c.step, nsteps)) {
+    for (int64_t i = 0; i < nsteps; ++i) c.t += c.dt;  // same rounding as FF's clock.t += dt per step
+    c.step += nsteps;
+    return;
+  }
   for (int64_t i = 0; i < nsteps; ++i) {
     run_velocity_providers(h);
     h->engine->step_once(c.step);
@@ -346,9 +355,17 @@ int32_t ptf_create(const ptf_desc* d, ptf_handle** out) {
     build_context(h, d);
     std::string why;
     int want = d->engine;
+    const bool one_d = h->ctx.g.ndim == 1;
     if (want == PTF_ENGINE_FUSED) {
-      if (!fused_engine_supports(h->ctx, &why)) throw Error(PTF_EUNSUPPORTED, "fused engine: " + why);
-      h->engine = make_fused_engine(h->ctx);
+      if (one_d) {
+        if (!fused1d_engine_supports(h->ctx, &why)) throw Error(PTF_EUNSUPPORTED, "fused engine: " + why);
+        h->engine = make_fused1d_engine(h->ctx);
+      } else {
+        if (!fused_engine_supports(h->ctx, &why)) throw Error(PTF_EUNSUPPORTED, "fused engine: " + why);
+        h->engine = make_fused_engine(h->ctx);
+      }
+    } else if (want == PTF_ENGINE_AUTO && one_d && fused1d_engine_supports(h->ctx, &why)) {
+      h->engine = make_fused1d_engine(h->ctx);
     } else if (want == PTF_ENGINE_AUTO && !h->ctx.g.slab && fused_engine_supports(h->ctx, &why)) {
       h->engine = make_fused_engine(h->ctx);
     } else {

@@ -135,6 +135,12 @@ class Engine {
   virtual void set_sol(const double* s_host) = 0;
   virtual void get_sol(double* s_host) = 0;
   virtual void step_once(int64_t step_index) = 0;  // enqueue one full time step on the stream
+  // enqueue n steps at once when the engine can (velocity unchanged between them); false = not supported
+  virtual bool step_many(int64_t first_step, int64_t n) {
+    (void)first_step;
+    (void)n;
+    return false;
+  }
   virtual void on_dt_changed() = 0;
   virtual void diag(double* mean_c, double* var_c, double* max_abs_sol) = 0;
   virtual float time_kernel(const char* name, int reps) = 0;
@@ -160,6 +166,8 @@ std::unique_ptr<Engine> make_cufft_engine(Context& ctx);
 std::unique_ptr<Engine> make_fused_engine(Context& ctx);  // throws PTF_EUNSUPPORTED when the grid does not qualify
 bool fused_engine_supports(const Context& ctx, std::string* why);
 void selftest_fft(int n, int dir, int count, const double* in_host, double* out_host);
+std::unique_ptr<Engine> make_fused1d_engine(Context& ctx);
+bool fused1d_engine_supports(const Context& ctx, std::string* why);
 
 }  // namespace ptf
 

@@ -270,3 +270,46 @@ def test_full_size_engines_agree_and_variance_decays():
         last = v
     assert rel_l2(pc.updatevars(), pf.updatevars()) <= 20 * TOL_STEP
     assert abs(pc.diagnostics()["variance_c"] - last) <= 1e-12 * last
+
+
+# ------------------------------------------------------------------------------------------
+# fused 1-D engine: whole steps (or many steps) in one launch by one CTA
+# ------------------------------------------------------------------------------------------
+STEPPERS_1D = ["ForwardEuler", "RK4", "ETDRK4", "LSRK54", "AB3", "FilteredRK4", "FilteredETDRK4", "FilteredAB3"]
+
+
+@pytest.mark.parametrize("stepper", STEPPERS_1D)
+@pytest.mark.parametrize("nx", [16, 128, 2048])
+def test_fused_1d_all_steppers(stepper, nx):
+    n, L = (nx,), (2 * np.pi,)
+    (x,) = _pts(n, L)
+    u = 0.05 + 0.02 * np.sin(x)
+    kw = dict(n=n, L=L, kappa=(0.01,), dt=0.02 if nx <= 128 else 2e-5, stepper=stepper, velocity=[np.ascontiguousarray(u)],
+              steady=True, kappa_h=1e-9 if nx <= 128 else 0.0, n_kappa_h=2)
+    _compare(kw, np.exp(-x ** 2 / (2 * 0.15 ** 2)), [1, 2, 5, 40])
+
+
+def test_fused_1d_time_varying_and_batch_and_dealias():
+    n, L = (128,), (2 * np.pi,)
+    (x,) = _pts(n, L)
+    u = lambda x, t: 0.05 * t + 0.01 * np.cos(x) * (1 + t)
+    kw = dict(n=n, L=L, kappa=(0.0,), dt=0.002, stepper="RK4", velocity=[u], steady=False)
+    _compare(kw, 0.1 * np.exp(-x ** 2 / (2 * 0.2 ** 2)), [1, 3, 10])
+    B = 3
+    cx = np.linspace(-1, 1, B).reshape(B, 1)
+    kw = dict(n=n, L=L, kappa=(0.01,), dt=0.01, stepper="RK4", velocity=[np.full(n, 0.3)], steady=True, nbatch=B,
+              dealias=True)
+    rng = np.random.default_rng(2)
+    _compare(kw, rng.standard_normal((B, 128)) + np.exp(-(x - cx) ** 2), [1, 4])
+
+
+def test_fused_1d_is_one_launch_per_call():
+    P = _P()
+    prob = P.Problem(P.B200(engine="fused"), P.OneDAdvectingFlow(u=lambda x: 0.05 + 0 * x), nx=128, kappa=0.01, dt=0.02)
+    x = P.gridpoints(prob.grid)
+    prob.set_c(np.exp(-x ** 2 / (2 * 0.15 ** 2)))
+    own0, lib0 = prob.launch_count()
+    prob.stepforward(500)
+    own1, lib1 = prob.launch_count()
+    assert own1 - own0 == 1 and lib1 == lib0            # 500 RK4 steps = 2000 stages = one kernel launch, no cuFFT
+    assert prob.clock.step == 500 and abs(prob.clock.t - 10.0) < 1e-12
