@@ -166,7 +166,7 @@ def run_reference(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dtm / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"cellularflow_{nx}x{nx}_RK4_kappa0.1 (BASELINE configs[1])", "nx": nx, "ny": nx,
-                       "stepper": "RK4", "dt": w["dt"]},
+                       "stepper": "RK4", "dt": w["dt"], "rk4_steps_per_step": 1},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
