@@ -222,20 +222,50 @@ __global__ void __launch_bounds__(256) k_diag(const double2* __restrict__ s, Spe
 // ---- slab transposes (3-D, one process per GPU).  blk = nzl*nyl*nkr complex values go to / come from each peer.
 // pack:   T2[r][zl][jl][kx] = T1[zl][r*nyl + jl][kx]       (after the local 2-D r2c, before the all-to-all)
 // unpack: T1[zl][s*nyl + jl][kx] = T2[s][zl][jl][kx]       (after the all-to-all, before the local 2-D c2r)
-__global__ void __launch_bounds__(256) k_slab_pack(const double2* __restrict__ T1, double2* __restrict__ T2, int64_t nkr,
-                                                   int64_t nyl, int64_t nzl, int64_t P, int unpack, int64_t z0,
-                                                   int64_t nzc) {
-  int64_t ny = nyl * P;
-  int64_t rows = nzc * ny;  // (zl, j) rows of nkr, planes z0 .. z0+nzc-1
-  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-    int64_t zl = z0 + row / ny, j = row % ny;
-    int64_t r = j / nyl, jl = j % nyl;
-    const int64_t a = (zl * ny + j) * nkr;                    // index in T1
-    const int64_t b = ((r * nzl + zl) * nyl + jl) * nkr;      // index in T2
-    if (!unpack)
-      for (int64_t k = threadIdx.x; k < nkr; k += blockDim.x) T2[b + k] = T1[a + k];
-    else
-      for (int64_t k = threadIdx.x; k < nkr; k += blockDim.x) T2[a + k] = T1[b + k];
+// MODE 0 pack, 1 unpack, 2 unpack fused with the x/y derivatives of the shared partial inverse transform:
+//        f[zl][j][kx] = i*kx*v,  dy[zl][j][kx] = i*ky_j*v   with v = T2[s][zl][jl][kx].
+// One warp copies RPW consecutive rows of nkr values, RPW loads in flight per thread before the first store.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_slab_pack(const double2* __restrict__ src, double2* __restrict__ dst,
+                                                   double2* __restrict__ dy, const double* __restrict__ kxt,
+                                                   const double* __restrict__ kyt, int64_t nkr, int64_t nyl,
+                                                   int64_t nzl, int64_t P, int64_t z0, int64_t nzc) {
+  constexpr int RPW = 4;
+  const int64_t ny = nyl * P;
+  const int64_t rows = nzc * ny;  // (zl, j) rows of nkr values, planes z0 .. z0+nzc-1
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row0 = warp * RPW; row0 < rows; row0 += nwarps * RPW) {
+    int64_t a[RPW], b[RPW];
+    double ky[RPW];
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) {
+      const int64_t row = row0 + q < rows ? row0 + q : rows - 1;
+      const int64_t zl = z0 + row / ny, j = row % ny;
+      const int64_t r = j / nyl, jl = j % nyl;
+      a[q] = (zl * ny + j) * nkr;                // plane layout   [zl][j][kx]
+      b[q] = ((r * nzl + zl) * nyl + jl) * nkr;  // peer-block layout [r][zl][jl][kx]
+      ky[q] = MODE == 2 ? kyt[j] : 0.0;
+    }
+    for (int64_t k = lane; k < nkr; k += 32) {
+      double2 v[RPW];
+#pragma unroll
+      for (int q = 0; q < RPW; ++q) v[q] = __ldcg(src + (MODE == 0 ? a[q] : b[q]) + k);
+      const double kx = MODE == 2 ? kxt[k] : 0.0;
+#pragma unroll
+      for (int q = 0; q < RPW; ++q) {
+        if (row0 + q >= rows) break;
+        if (MODE == 0) {
+          __stcg(dst + b[q] + k, v[q]);
+        } else if (MODE == 1) {
+          __stcg(dst + a[q] + k, v[q]);
+        } else {
+          __stcg(dst + a[q] + k, make_double2(-kx * v[q].y, kx * v[q].x));
+          __stcg(dy + a[q] + k, make_double2(-ky[q] * v[q].y, ky[q] * v[q].x));
+        }
+      }
+    }
   }
 }
 
@@ -454,7 +484,7 @@ class CufftEngine final : public Engine {
     PTF_CUFFT(cufftExecD2Z(plan_fwd, real, reinterpret_cast<cufftDoubleComplex*>(T1.p)));
     pt.end();
     pt.begin(1);
-    k_slab_pack<<<1184, 256, 0, ctx.stream>>>(T1.p, T2.p, g.nkr, g.nyl, g.nzl, g.P, 0, 0, g.nzl);
+    k_slab_pack<0><<<2368, 256, 0, ctx.stream>>>(T1.p, T2.p, nullptr, nullptr, nullptr, g.nkr, g.nyl, g.nzl, g.P, 0, g.nzl);
     pt.end();
     ++own_launches;
     pt.begin(2);
@@ -482,7 +512,7 @@ class CufftEngine final : public Engine {
     all_to_all(spec, T2.p);  // chunk r of [nz][nyl][nkr] is the z-range of rank r: no packing on the send side
     pt.end();
     pt.begin(1);
-    k_slab_pack<<<1184, 256, 0, ctx.stream>>>(T2.p, T1.p, g.nkr, g.nyl, g.nzl, g.P, 1, 0, g.nzl);
+    k_slab_pack<1><<<2368, 256, 0, ctx.stream>>>(T2.p, T1.p, nullptr, nullptr, nullptr, g.nkr, g.nyl, g.nzl, g.P, 0, g.nzl);
     pt.end();
     ++own_launches;
     pt.begin(0);
@@ -595,18 +625,14 @@ class CufftEngine final : public Engine {
     PTF_CUDA(cudaEventRecord(ev[3], s_comm));
     // field 0 arrived: unpack, x/y derivatives in the plane layout, two batched 2-D c2r
     PTF_CUDA(cudaStreamWaitEvent(ctx.stream, ev[1], 0));
-    k_slab_pack<<<1184, 256, 0, ctx.stream>>>(T2.p, T1.p, g.nkr, g.nyl, g.nzl, g.P, 1, 0, g.nzl);
-    {
-      int tx = pow2_at_least(g.nkr, 256), ty = 256 / tx;
-      dim3 b2(tx, ty, 1), g2((unsigned)((g.ny * g.nzl + ty - 1) / ty), 1, 1);
-      k_deriv_xy_planes<<<g2, b2, 0, ctx.stream>>>(T1.p, dh[1].p, ctx.ax.kx, ctx.ax.ky, g.nkr, g.ny, g.nzl);
-    }
-    own_launches += 2;
+    // unpack fused with the x/y derivatives (applied in the plane layout, so they never travel)
+    k_slab_pack<2><<<2368, 256, 0, ctx.stream>>>(T2.p, T1.p, dh[1].p, ctx.ax.kx, ctx.ax.ky, g.nkr, g.nyl, g.nzl, g.P, 0, g.nzl);
+    own_launches += 1;
     PTF_CUFFT(cufftExecZ2D(plan_inv, Z(T1.p), gr[0].p));
     PTF_CUFFT(cufftExecZ2D(plan_inv, Z(dh[1].p), gr[1].p));
     // field 2 arrived
     PTF_CUDA(cudaStreamWaitEvent(ctx.stream, ev[3], 0));
-    k_slab_pack<<<1184, 256, 0, ctx.stream>>>(T3.p, T1.p, g.nkr, g.nyl, g.nzl, g.P, 1, 0, g.nzl);
+    k_slab_pack<1><<<2368, 256, 0, ctx.stream>>>(T3.p, T1.p, nullptr, nullptr, nullptr, g.nkr, g.nyl, g.nzl, g.P, 0, g.nzl);
     ++own_launches;
     PTF_CUFFT(cufftExecZ2D(plan_inv, Z(T1.p), gr[2].p));
     lib_calls += 7;
@@ -624,7 +650,7 @@ class CufftEngine final : public Engine {
     for (int c = 0; c < nch; ++c) {
       const int64_t z0 = c * nzc;
       PTF_CUFFT(cufftExecD2Z(plan_fwd_chunk, gr[0].p + z0 * g.nx * g.ny, Z(T1.p + z0 * g.ny * g.nkr)));
-      k_slab_pack<<<1184, 256, 0, ctx.stream>>>(T1.p, T2.p, g.nkr, g.nyl, g.nzl, g.P, 0, z0, nzc);
+      k_slab_pack<0><<<2368, 256, 0, ctx.stream>>>(T1.p, T2.p, nullptr, nullptr, nullptr, g.nkr, g.nyl, g.nzl, g.P, z0, nzc);
       ++own_launches;
       fork_comm_after(ev[4 + c]);
       all_to_all(T2.p, dh[0].p, s_comm, z0, nzc);
