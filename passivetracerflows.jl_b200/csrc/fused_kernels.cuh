@@ -764,17 +764,20 @@ void allow_smem(K kernel, size_t bytes) {
   PTF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 
-// CTA size for a launch of `items` transforms-groups: the largest NT in {256,128,64} (>= T) that still yields at
-// least 2 CTAs per SM, else the smallest allowed.
+// CTA size for a launch of `items` transform groups (measured on B200, profiles/r01_fft_core_experiments.md §7):
+// four independent 128-thread CTAs per SM beat two 256-thread CTAs (more independent phase streams), so 128 threads
+// is the default whenever a transform fits (N <= 2048); tiny launches drop to 64 threads to create enough CTAs to
+// cover the 148 SMs; 4096-point transforms need 256 threads.
 template <int N>
 int pick_nt(long items, int n_sm) {
   constexpr int T = Cfg<N>::T;
-  for (int nt : {256, 128, 64}) {
-    if (nt < T) break;
-    long ctas = (items + nt / T - 1) / (nt / T);
-    if (ctas >= 2L * n_sm || nt == 64 || nt / 2 < T) return nt;
-  }
-  return T > 64 ? T : 64;
+  const char* fe = std::getenv("PTF_NT");  // experiment knob: force the CTA size (clamped to >= T)
+  const int forced = fe ? std::atoi(fe) : 0;
+  if (forced == 64 || forced == 128 || forced == 256) return forced < T ? T : forced;
+  if (T > 128) return 256;
+  const long ctas128 = (items + 128 / T - 1) / (128 / T);
+  if (ctas128 >= 2L * n_sm || T > 64) return 128;
+  return 64;
 }
 
 template <int NY, int NT>
