@@ -415,7 +415,6 @@ bool fused_engine_supports(const Context& ctx, std::string* why) {
   };
   if (ctx.g.ndim != 2) return no("only 2-D problems (1-D / 3-D run on the cuFFT engine)");
   if (!is_fused_size(ctx.g.nx) || !is_fused_size(ctx.g.ny)) return no("nx and ny must be powers of two in [256, 4096]");
-  if (ctx.d.dealias) return no("dealias option is served by the cuFFT engine");
   if (ctx.g.B > 65535) return no("batch too large for one launch");
   return true;
 }

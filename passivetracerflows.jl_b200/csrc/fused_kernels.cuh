@@ -71,9 +71,9 @@ __device__ __noinline__ double filter_slow(double fx, double fy, double f_inner,
 // ---- RK4 family (FF RK4substeps!/RK4update!).  N^ (t_nh) and the new stage state s' (t_w) live in TMEM, so a
 // ---- batch of NB elements can have all 3*NB of its 16-byte state loads in flight at once (2 memory round trips
 // ---- per column instead of 4) and nothing accumulates in registers.
-template <int NY, int MODE>
+template <int NY, int MODE, bool DM>
 __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_t t_w, size_t col, int t, double kx,
-                                          bool active, const double (&fl)[16]) {
+                                          bool active, const double (&fl)[16], int kr) {
   constexpr int T = Cfg<NY>::T, NB = 8;
   const double dt = a.C.dt;
 #pragma unroll
@@ -83,6 +83,8 @@ __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_
     for (int j = 0; j < NB; ++j) {
       const size_t i = col + t + T * (e0 + j);
       s0[j] = __ldcg(a.P.s0 + i);
+      // opt-in dealias!(sol) at the top of calcN: sol is read as if it had been masked in place at stage 1
+      if (DM && dealiased_out(a.ax, kr, t + T * (e0 + j), 0)) s0[j] = make_double2(0.0, 0.0);
       if (MODE != CM_RK4_S1) {
         ss[j] = __ldcg(a.P.s1 + i);
         ac[j] = __ldcg(a.P.acc + i);
@@ -99,10 +101,12 @@ __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_
         const double ky = a.ax.ky[l];
         const double L = lin_op(a.ax, kx, ky, 0.0);
         const double2 Nh = nh[jj];
+        const bool dm = DM && dealiased_out(a.ax, kr, l, 0);
         double2 next;
         if (MODE == CM_RK4_S1) {
           double2 k = cadd(Nh, cmul_r(s0[j], L));
           next = cadd(s0[j], cmul_r(k, dt / 2));
+          if (dm) next = make_double2(0.0, 0.0);   // the next calcN masks its stage state in place
           if (active) {
             __stcg(a.P.acc + i, cdiv_r(k, 6.0));
             __stcg(a.P.s1 + i, next);
@@ -110,6 +114,7 @@ __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_
         } else if (MODE == CM_RK4_S2 || MODE == CM_RK4_S3) {
           double2 k = cadd(Nh, cmul_r(ss[j], L));
           next = cadd(s0[j], cmul_r(k, MODE == CM_RK4_S2 ? dt / 2 : dt));
+          if (dm) next = make_double2(0.0, 0.0);
           if (active) {
             __stcg(a.P.acc + i, cadd(ac[j], cdiv_r(k, 3.0)));
             __stcg(a.P.s1 + i, next);
@@ -119,7 +124,8 @@ __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_
           double2 sum = cadd(ac[j], cdiv_r(k, 6.0));
           next = cadd(s0[j], cmul_r(sum, dt));
           if (a.C.filtered) next = cmul_r(next, fl[e]);
-          if (active) __stcg(a.P.s0 + i, next);
+          if (active) __stcg(a.P.s0 + i, next);  // stored unmasked (as the reference leaves sol after the update) ...
+          if (dm) next = make_double2(0.0, 0.0); // ... but the next step's first calcN sees it masked
         }
         tmem::st1(t_w + 4 * e, make_double2(next.x * a.inv_n, next.y * a.inv_n));
       }
@@ -129,9 +135,9 @@ __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_
 }
 
 // ---- ETDRK4 family (FF ETDRK4substeps!/ETDRK4update!)
-template <int NY, int MODE>
+template <int NY, int MODE, bool DM>
 __device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16], double2 (&w)[16], size_t col,
-                                          size_t ccol, int t, double kx, bool active, const double (&fl)[16]) {
+                                          size_t ccol, int t, double kx, bool active, const double (&fl)[16], int kr) {
   constexpr int T = Cfg<NY>::T, NB = 4;
 #pragma unroll
   for (int e0 = 0; e0 < 16; e0 += NB) {
@@ -140,8 +146,10 @@ __device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16]
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       const size_t i = col + t + T * (e0 + j), ci = ccol + t + T * (e0 + j);
+      const bool dmj = DM && dealiased_out(a.ax, kr, t + T * (e0 + j), 0);
       if (MODE == CM_ETD_S1 || MODE == CM_ETD_S2) {
         sa[j] = __ldcg(a.P.s0 + i);
+        if (dmj) sa[j] = make_double2(0.0, 0.0);
         c0[j] = __ldcg(a.P.E2 + ci);
         c1[j] = __ldcg(a.P.zeta + ci);
       } else if (MODE == CM_ETD_S3) {
@@ -152,6 +160,7 @@ __device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16]
         c1[j] = __ldcg(a.P.zeta + ci);
       } else {
         sa[j] = __ldcg(a.P.s0 + i);
+        if (dmj) sa[j] = make_double2(0.0, 0.0);
         n1[j] = __ldcg(a.P.n1 + i);
         ac[j] = __ldcg(a.P.acc + i);
         c0[j] = __ldcg(a.P.E + ci);
@@ -165,15 +174,18 @@ __device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16]
       const int e = e0 + j, l = t + T * e;
       const size_t i = col + l;
       const double2 Nh = v[out_slot<NY>(e)];
+      const bool dm = DM && dealiased_out(a.ax, kr, l, 0);
       double2 next;
       if (MODE == CM_ETD_S1) {
         next = cadd(cmul_r(sa[j], c0[j]), cmul_r(Nh, c1[j]));
+        if (dm) next = make_double2(0.0, 0.0);
         if (active) {
           __stcg(a.P.n1 + i, Nh);
           __stcg(a.P.s1 + i, next);
         }
       } else if (MODE == CM_ETD_S2) {
         next = cadd(cmul_r(sa[j], c0[j]), cmul_r(Nh, c1[j]));
+        if (dm) next = make_double2(0.0, 0.0);
         if (active) {
           __stcg(a.P.acc + i, Nh);
           __stcg(a.P.s2 + i, next);
@@ -181,6 +193,7 @@ __device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16]
       } else if (MODE == CM_ETD_S3) {
         double2 tt = make_double2(2 * Nh.x - n1[j].x, 2 * Nh.y - n1[j].y);
         next = cadd(cmul_r(sa[j], c0[j]), cmul_r(tt, c1[j]));
+        if (dm) next = make_double2(0.0, 0.0);
         if (active) {
           __stcg(a.P.acc + i, cadd(ac[j], Nh));
           __stcg(a.P.s2 + i, next);
@@ -193,6 +206,7 @@ __device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16]
         if (a.C.filtered) r = cmul_r(r, fl[e]);
         next = r;
         if (active) __stcg(a.P.s0 + i, next);
+        if (dm) next = make_double2(0.0, 0.0);
       }
       w[e] = make_double2(next.x * a.inv_n, next.y * a.inv_n);
     }
@@ -201,7 +215,8 @@ __device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16]
 
 // NT = threads per CTA (64, 128 or 256; >= T).  Small problems use small CTAs so that enough CTAs exist to fill the
 // 148 SMs; TMEM is allocated 128 columns per warp-quarter, i.e. 128 columns per CTA up to 4 warps, 256 for 8 warps.
-template <int NY, int FAM, bool HAS_IN, bool HAS_OUT, int NT>
+// DM = the opt-in dealias!(sol) mask is compiled in (kept out of the default kernels: it costs registers)
+template <int NY, int FAM, bool HAS_IN, bool HAS_OUT, int NT, bool DM = false>
 __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
   constexpr int T = Cfg<NY>::T, F = NT / T, PADN = Cfg<NY>::PADN;
   constexpr int TCOLS = NT > 128 ? 256 : 128;
@@ -277,10 +292,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
       for (int e = 0; e < 16; ++e) tmem::st1(t_nh + 4 * e, v[out_slot<NY>(e)]);
       tmem::wait_st();
       switch (a.C.mode) {
-        case CM_RK4_S1: rk4_stage<NY, CM_RK4_S1>(a, t_nh, t_w, col, t, kx, active, fl); break;
-        case CM_RK4_S2: rk4_stage<NY, CM_RK4_S2>(a, t_nh, t_w, col, t, kx, active, fl); break;
-        case CM_RK4_S3: rk4_stage<NY, CM_RK4_S3>(a, t_nh, t_w, col, t, kx, active, fl); break;
-        default: rk4_stage<NY, CM_RK4_S4>(a, t_nh, t_w, col, t, kx, active, fl); break;
+        case CM_RK4_S1: rk4_stage<NY, CM_RK4_S1, DM>(a, t_nh, t_w, col, t, kx, active, fl, kr); break;
+        case CM_RK4_S2: rk4_stage<NY, CM_RK4_S2, DM>(a, t_nh, t_w, col, t, kx, active, fl, kr); break;
+        case CM_RK4_S3: rk4_stage<NY, CM_RK4_S3, DM>(a, t_nh, t_w, col, t, kx, active, fl, kr); break;
+        default: rk4_stage<NY, CM_RK4_S4, DM>(a, t_nh, t_w, col, t, kx, active, fl, kr); break;
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -291,18 +306,23 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
       }
     } else if (FAM == FAM_ETD) {
       switch (a.C.mode) {
-        case CM_ETD_S1: etd_stage<NY, CM_ETD_S1>(a, v, w, col, ccol, t, kx, active, fl); break;
-        case CM_ETD_S2: etd_stage<NY, CM_ETD_S2>(a, v, w, col, ccol, t, kx, active, fl); break;
-        case CM_ETD_S3: etd_stage<NY, CM_ETD_S3>(a, v, w, col, ccol, t, kx, active, fl); break;
-        default: etd_stage<NY, CM_ETD_S4>(a, v, w, col, ccol, t, kx, active, fl); break;
+        case CM_ETD_S1: etd_stage<NY, CM_ETD_S1, DM>(a, v, w, col, ccol, t, kx, active, fl, kr); break;
+        case CM_ETD_S2: etd_stage<NY, CM_ETD_S2, DM>(a, v, w, col, ccol, t, kx, active, fl, kr); break;
+        case CM_ETD_S3: etd_stage<NY, CM_ETD_S3, DM>(a, v, w, col, ccol, t, kx, active, fl, kr); break;
+        default: etd_stage<NY, CM_ETD_S4, DM>(a, v, w, col, ccol, t, kx, active, fl, kr); break;
       }
     } else {
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int l = t + T * e;
         double2 nx = make_double2(0.0, 0.0);
-        if (active)
+        const bool dm = DM && dealiased_out(a.ax, kr, l, 0);
+        if (active) {
+          // ForwardEuler / LSRK54 / AB3 evaluate calcN at sol itself: dealias!(sol) acts in place before the combine
+          if (dm) a.P.s0[col + l] = make_double2(0.0, 0.0);
           nx = combine_at<CMASK_OTHER>(a.P, a.C, a.ax, col + l, ccol + l, kx, a.ax.ky[l], 0.0, v[out_slot<NY>(e)]);
+        }
+        if (dm) nx = make_double2(0.0, 0.0);
         w[e] = make_double2(nx.x * a.inv_n, nx.y * a.inv_n);
       }
     }
@@ -310,6 +330,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       double2 s = __ldcg(a.next_state + col + t + T * e);
+      if (DM && dealiased_out(a.ax, kr, t + T * e, 0)) s = make_double2(0.0, 0.0);
       w[e] = make_double2(s.x * a.inv_n, s.y * a.inv_n);
     }
   }
@@ -340,6 +361,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
     for (int e = 0; e < 16; ++e) {
       const int l = t + T * e;
       double2 s = __ldcg(a.next_state + col + l);
+      if (DM && dealiased_out(a.ax, kr, l, 0)) s = make_double2(0.0, 0.0);
       double ky = a.ax.ky[l] * a.inv_n;
       w[e] = make_double2(-ky * s.y, ky * s.x);
     }
@@ -783,10 +805,14 @@ int pick_nt(long items, int n_sm) {
 template <int NY, int NT>
 void prep_y_nt() {  // opt in to > 48 KB dynamic shared memory (per device, so done at engine construction)
   if constexpr (NT >= Cfg<NY>::T) {
-    allow_smem(k_fused_y<NY, FAM_RK4, false, true, NT>, y_smem<NY, NT>() + g_smem_pad);
-    allow_smem(k_fused_y<NY, FAM_RK4, true, true, NT>, y_smem<NY, NT>() + g_smem_pad);
-    allow_smem(k_fused_y<NY, FAM_ETD, true, true, NT>, y_smem<NY, NT>() + g_smem_pad);
-    allow_smem(k_fused_y<NY, FAM_OTHER, true, true, NT>, y_smem<NY, NT>() + g_smem_pad);
+    allow_smem(k_fused_y<NY, FAM_RK4, false, true, NT, false>, y_smem<NY, NT>() + g_smem_pad);
+    allow_smem(k_fused_y<NY, FAM_RK4, true, true, NT, false>, y_smem<NY, NT>() + g_smem_pad);
+    allow_smem(k_fused_y<NY, FAM_ETD, true, true, NT, false>, y_smem<NY, NT>() + g_smem_pad);
+    allow_smem(k_fused_y<NY, FAM_OTHER, true, true, NT, false>, y_smem<NY, NT>() + g_smem_pad);
+    allow_smem(k_fused_y<NY, FAM_RK4, false, true, NT, true>, y_smem<NY, NT>() + g_smem_pad);
+    allow_smem(k_fused_y<NY, FAM_RK4, true, true, NT, true>, y_smem<NY, NT>() + g_smem_pad);
+    allow_smem(k_fused_y<NY, FAM_ETD, true, true, NT, true>, y_smem<NY, NT>() + g_smem_pad);
+    allow_smem(k_fused_y<NY, FAM_OTHER, true, true, NT, true>, y_smem<NY, NT>() + g_smem_pad);
   }
 }
 template <int NY>
@@ -815,10 +841,17 @@ void launch_y_nt(bool has_in, int fam, const YArgs& a, int nb, cudaStream_t st) 
     constexpr int F = NT / Cfg<NY>::T;
     dim3 grid((a.nkr + F - 1) / F, nb, 1);
     size_t sm = y_smem<NY, NT>() + g_smem_pad;
-    if (!has_in) k_fused_y<NY, FAM_RK4, false, true, NT><<<grid, NT, sm, st>>>(a);
-    else if (fam == FAM_RK4) k_fused_y<NY, FAM_RK4, true, true, NT><<<grid, NT, sm, st>>>(a);
-    else if (fam == FAM_ETD) k_fused_y<NY, FAM_ETD, true, true, NT><<<grid, NT, sm, st>>>(a);
-    else k_fused_y<NY, FAM_OTHER, true, true, NT><<<grid, NT, sm, st>>>(a);
+    if (a.ax.dealias) {
+      if (!has_in) k_fused_y<NY, FAM_RK4, false, true, NT, true><<<grid, NT, sm, st>>>(a);
+      else if (fam == FAM_RK4) k_fused_y<NY, FAM_RK4, true, true, NT, true><<<grid, NT, sm, st>>>(a);
+      else if (fam == FAM_ETD) k_fused_y<NY, FAM_ETD, true, true, NT, true><<<grid, NT, sm, st>>>(a);
+      else k_fused_y<NY, FAM_OTHER, true, true, NT, true><<<grid, NT, sm, st>>>(a);
+      return;
+    }
+    if (!has_in) k_fused_y<NY, FAM_RK4, false, true, NT, false><<<grid, NT, sm, st>>>(a);
+    else if (fam == FAM_RK4) k_fused_y<NY, FAM_RK4, true, true, NT, false><<<grid, NT, sm, st>>>(a);
+    else if (fam == FAM_ETD) k_fused_y<NY, FAM_ETD, true, true, NT, false><<<grid, NT, sm, st>>>(a);
+    else k_fused_y<NY, FAM_OTHER, true, true, NT, false><<<grid, NT, sm, st>>>(a);
   }
 }
 template <int NY>

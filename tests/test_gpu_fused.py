@@ -313,3 +313,15 @@ def test_fused_1d_is_one_launch_per_call():
     own1, lib1 = prob.launch_count()
     assert own1 - own0 == 1 and lib1 == lib0            # 500 RK4 steps = 2000 stages = one kernel launch, no cuFFT
     assert prob.clock.step == 500 and abs(prob.clock.t - 10.0) < 1e-12
+
+
+@pytest.mark.parametrize("stepper", ["RK4", "ETDRK4", "LSRK54", "AB3", "FilteredRK4"])
+def test_fused_dealias_option(stepper):
+    # opt-in dealias!(sol) at the top of every calcN (FourierFlows' box mask), fused into the column kernel
+    n, L = (256, 512), (2 * np.pi, 2 * np.pi)
+    rng = np.random.default_rng(7)
+    x, y = _pts(n, L)
+    c0 = rng.standard_normal((n[1], n[0]))        # white noise: every mode populated, incl. the masked ones
+    vel = [np.ascontiguousarray(0.3 * np.cos(x) * np.sin(y)), np.ascontiguousarray(-0.3 * np.sin(x) * np.cos(y))]
+    kw = dict(n=n, L=L, kappa=(0.01, 0.01), dt=2e-4, stepper=stepper, velocity=vel, steady=True, dealias=True)
+    _compare(kw, c0, [1, 2, 5])
