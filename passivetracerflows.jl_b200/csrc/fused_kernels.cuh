@@ -108,7 +108,7 @@ __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_
           next = cadd(s0[j], cmul_r(k, dt / 2));
           if (dm) next = make_double2(0.0, 0.0);   // the next calcN masks its stage state in place
           if (active) {
-            __stcg(a.P.acc + i, cdiv_r(k, 6.0));
+            __stcg(a.P.acc + i, cmul_r(k, 1.0 / 6.0));
             __stcg(a.P.s1 + i, next);
           }
         } else if (MODE == CM_RK4_S2 || MODE == CM_RK4_S3) {
@@ -116,12 +116,12 @@ __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_
           next = cadd(s0[j], cmul_r(k, MODE == CM_RK4_S2 ? dt / 2 : dt));
           if (dm) next = make_double2(0.0, 0.0);
           if (active) {
-            __stcg(a.P.acc + i, cadd(ac[j], cdiv_r(k, 3.0)));
+            __stcg(a.P.acc + i, cadd(ac[j], cmul_r(k, 1.0 / 3.0)));
             __stcg(a.P.s1 + i, next);
           }
         } else {  // CM_RK4_S4
           double2 k = cadd(Nh, cmul_r(ss[j], L));
-          double2 sum = cadd(ac[j], cdiv_r(k, 6.0));
+          double2 sum = cadd(ac[j], cmul_r(k, 1.0 / 6.0));
           next = cadd(s0[j], cmul_r(sum, dt));
           if (a.C.filtered) next = cmul_r(next, fl[e]);
           if (active) __stcg(a.P.s0 + i, next);  // stored unmasked (as the reference leaves sol after the update) ...

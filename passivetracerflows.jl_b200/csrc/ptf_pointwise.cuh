@@ -118,7 +118,7 @@ __device__ __forceinline__ double2 combine_at(const CombinePtrs& P, const Combin
       double L = lin_op(ax, kx, ky, kz);
       double2 s0 = P.s0[i];
       double2 k = cadd(Nh, cmul_r(s0, L));
-      P.acc[i] = cdiv_r(k, 6.0);
+      P.acc[i] = cmul_r(k, 1.0 / 6.0);
       next = cadd(s0, cmul_r(k, dt / 2));
       P.s1[i] = next;
     } break;
@@ -127,7 +127,7 @@ __device__ __forceinline__ double2 combine_at(const CombinePtrs& P, const Combin
       double L = lin_op(ax, kx, ky, kz);
       double2 ss = P.s1[i];
       double2 k = cadd(Nh, cmul_r(ss, L));
-      P.acc[i] = cadd(P.acc[i], cdiv_r(k, 3.0));
+      P.acc[i] = cadd(P.acc[i], cmul_r(k, 1.0 / 3.0));
       double h = (A.mode == CM_RK4_S2) ? dt / 2 : dt;
       next = cadd(P.s0[i], cmul_r(k, h));
       P.s1[i] = next;
@@ -136,7 +136,7 @@ __device__ __forceinline__ double2 combine_at(const CombinePtrs& P, const Combin
       double L = lin_op(ax, kx, ky, kz);
       double2 ss = P.s1[i];
       double2 k = cadd(Nh, cmul_r(ss, L));
-      double2 sum = cadd(P.acc[i], cdiv_r(k, 6.0));
+      double2 sum = cadd(P.acc[i], cmul_r(k, 1.0 / 6.0));
       double2 r = cadd(P.s0[i], cmul_r(sum, dt));
       if (A.filtered) f = filter_val(ax, kx, ky, kz);
       next = cmul_r(r, f);
