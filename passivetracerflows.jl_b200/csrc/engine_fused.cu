@@ -66,8 +66,8 @@ class FusedEngine final : public Engine {
       tune_ablate_x = env_int("PTF_ABLATE_X", 0);
       // measured on B200 at 4096^2 (profiles/r01_fft_core_experiments.md): -2 % step time; only applied to launches
       // of >= 4 waves (see run_x / yargs), where an 8-10 us head start is negligible
-      tune_stagger_x = env_int("PTF_STAGGER_X", 15000);
-      tune_stagger_y = env_int("PTF_STAGGER_Y", 20000);
+      tune_stagger_x = env_int("PTF_STAGGER_X", 20000);
+      tune_stagger_y = env_int("PTF_STAGGER_Y", 25000);
       PTF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx.device));
       tune_ablate_y = env_int("PTF_ABLATE_Y", 0);
     }

@@ -74,7 +74,7 @@ __device__ __noinline__ double filter_slow(double fx, double fy, double f_inner,
 template <int NY, int MODE, bool DM>
 __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_t t_w, size_t col, int t, double kx,
                                           bool active, const double (&fl)[16], int kr) {
-  constexpr int T = Cfg<NY>::T, NB = 8;
+  constexpr int T = Cfg<NY>::T, NB = 4;
   const double dt = a.C.dt;
 #pragma unroll
   for (int e0 = 0; e0 < 16; e0 += NB) {
