@@ -257,10 +257,14 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
 
   if (HAS_IN) {
     double2 v[16];
-    const double2* P = a.Px + (size_t)b * NY * a.nkr + kr;
+    // P^x is stored blocked, [b][y/8][kr][y%8]: 8 consecutive y of one column are one 128-byte line, so this column
+    // read is fully coalesced (the row kernel pays with 32-byte full-sector stores, which do not stall its warps)
+    const double2* P = a.Px + (size_t)b * NY * a.nkr + (size_t)kr * 8;
 #pragma unroll
-    for (int e = 0; e < 16; ++e)
-      v[e] = __ldcg((a.ablate & 1) ? (a.Px + col + t + T * e) : (P + (size_t)(t + T * e) * a.nkr));  // L2-only: streamed once
+    for (int e = 0; e < 16; ++e) {
+      const int y = t + T * e;
+      v[e] = __ldcg((a.ablate & 1) ? (a.Px + col + y) : (P + (size_t)(y >> 3) * a.nkr * 8 + (y & 7)));  // L2-only
+    }
     // Pull the state columns the combine needs into L2 while the gather + forward FFT run (fire and forget).
     if ((t & 7) == 0) {
 #pragma unroll
@@ -282,9 +286,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
     if (a.pf_ahead > 0) {  // next wave's gather: one 32-byte sector per (y, kr') pair
       const int kr2 = kr_raw + a.pf_ahead * F;
       if (kr2 < a.nkr) {
-        const double2* P2 = a.Px + (size_t)b * NY * a.nkr + kr2;
+        const double2* P2 = a.Px + (size_t)b * NY * a.nkr + (size_t)kr2 * 8;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) prefetch_l2(P2 + (size_t)(t + T * e) * a.nkr);
+        for (int e = 0; e < 16; ++e) prefetch_l2(P2 + (size_t)((t + T * e) >> 3) * a.nkr * 8 + ((t + T * e) & 7));
       }
     }
     if (FAM == FAM_RK4) {
@@ -420,7 +424,7 @@ __device__ __forceinline__ void x_nyquist(int t, const double2* Ab, const double
 template <int NX, int VMODE>
 __device__ __forceinline__ void x_request_uv(const XArgs& a, size_t voff, int q, int t, uint32_t t_uv) {
   constexpr int T = Cfg<NX>::T;
-  constexpr int UB = 16;  // velocity request batch
+  constexpr int UB = 8;  // velocity request batch
   if (VMODE != 2) {
 #pragma unroll
     for (int h = 0; h < 16 / UB; ++h) {
@@ -552,20 +556,20 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
 #pragma unroll
   for (int e = 8; e < 16; ++e) sm[pad_idx(t + T * e)] = w[out_slot<NX>(e)];
   __syncthreads();
-  double2* P0 = a.Px + ((size_t)b * ny + 2 * pair) * a.nkr;
-  double2* P1 = P0 + a.nkr;
+  // blocked layout [b][y/8][kr][y%8]: rows y0 = 2*pair and y0+1 of one kr are 32 contiguous, 32-byte aligned bytes
+  const int y0 = 2 * pair;
+  double2* P0 = a.Px + (size_t)b * ny * a.nkr + (size_t)(y0 >> 3) * a.nkr * 8 + (y0 & 7);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int k = t + T * e;
     double2 W = w[out_slot<NX>(e)];
     double2 Wm = (e == 0 && t == 0) ? W : sm[pad_idx(NX - k)];
-    __stcg(P0 + k, make_double2(0.5 * (W.x + Wm.x), 0.5 * (W.y - Wm.y)));
-    __stcg(P1 + k, make_double2(0.5 * (W.y + Wm.y), 0.5 * (Wm.x - W.x)));
+    tmem::stg256(P0 + (size_t)k * 8, make_double2(0.5 * (W.x + Wm.x), 0.5 * (W.y - Wm.y)),
+                 make_double2(0.5 * (W.y + Wm.y), 0.5 * (Wm.x - W.x)));
   }
   if (t == 0) {
     double2 W = w[out_slot<NX>(8)];  // index 8*T = NX/2
-    P0[H] = make_double2(W.x, 0.0);
-    P1[H] = make_double2(W.y, 0.0);
+    tmem::stg256(P0 + (size_t)H * 8, make_double2(W.x, 0.0), make_double2(W.y, 0.0));
   }
   tmem::free_cta<TCOLS>(tbase);
 }
