@@ -180,6 +180,69 @@ int32_t ptf_diag(ptf_handle* h, double* mean_c, double* variance_c, double* max_
  * shared-memory FFT core; dir = -1 forward, +1 unnormalised inverse; interleaved complex128 host buffers */
 int32_t ptf_selftest_fft(int32_t n, int32_t dir, int32_t count, const double* in_host, double* out_host);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * MultiLayerQG flow solver: the flow that advects the tracer of Problem(MQGprob; ...) TAD.jl:225-250.
+ * The solver itself is GeophysicalFlows.MultiLayerQG (un-vendored, pinned 0.16 by Project.toml:25); these entry points
+ * replace the calls the reference makes into it:
+ *   ptf_mqg_create        MultiLayerQG.Problem(nlayers, dev; nx, Lx, f₀, H, b, U, μ, β, dt, stepper, aliased_fraction)
+ *                         examples/turbulent_advection-diffusion.jl:56-58
+ *   ptf_mqg_set_q         MultiLayerQG.set_q!(MQGprob, q₀)                      examples/…:69
+ *   ptf_mqg_step          stepforward!(params.MQGprob)                          examples/…:150
+ *   ptf_mqg_step_until    step_until!(MQGprob, tracer_release_time)             TAD.jl:238
+ *   ptf_mqg_updatevars    MultiLayerQG.updatevars!(MQGprob)                     TAD.jl:488, examples/…:151
+ *   ptf_mqg_get_var       MQGprob.vars.{u,v,q,ψ} (u, v read at TAD.jl:795-796; ψ at examples/…:110-118)
+ *   ptf_mqg_couple        ConstDiffTurbulentFlowParams(κ, η, tracer_release_time, MQGprob)   TAD.jl:485-491 — the
+ *                         layered tracer problem reads the flow's u, v (+U) on the device from then on
+ *   ptf_mqg_step_coupled  the example's loop body (examples/…:149-151), nsteps times, without host round trips
+ * Arrays: (nx, ny, nlayers) column-major float64 / (nx/2+1, ny, nlayers) complex128, x fastest.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define PTF_MQG_MAX_LAYERS 4
+
+typedef struct ptf_mqg_handle ptf_mqg_handle;
+
+typedef struct ptf_mqg_desc {
+  uint32_t struct_size;   /* = sizeof(ptf_mqg_desc); set by ptf_mqg_desc_init */
+  int32_t nlayers;        /* 1 .. PTF_MQG_MAX_LAYERS */
+  int64_t nx, ny;         /* even */
+  double Lx, Ly;
+  double f0, beta;        /* f₀, β */
+  const double* H;        /* [nlayers] rest depths */
+  const double* b;        /* [nlayers] Boussinesq buoyancies (nlayers >= 2) */
+  const double* U;        /* imposed zonal flow: [nlayers], or [nlayers][ny] when U_is_profile; NULL = 0 */
+  int32_t U_is_profile;
+  int32_t n_nu;           /* hyperviscosity order nν (>= 1) */
+  const double* eta;      /* [ny][nx] periodic topographic PV f₀h/H_n, or NULL */
+  double topographic_pv_gradient[2];
+  double mu, nu;          /* bottom drag μ, (hyper)viscosity ν */
+  double dt;
+  int32_t stepper;        /* PTF_STEPPER_* [| PTF_STEPPER_FILTERED] */
+  int32_t device;         /* CUDA ordinal; -1 = current */
+  double aliased_fraction;/* FF default 1/3; the reference's example uses 0 */
+  int32_t use_graph;
+  int32_t reserved[7];
+} ptf_mqg_desc;
+
+int32_t ptf_mqg_desc_init(ptf_mqg_desc* d); /* GeophysicalFlows defaults: 2 layers, 128², 2π, f₀ 1, β 0, RK4, dt 0.01 */
+int32_t ptf_mqg_create(const ptf_mqg_desc* d, ptf_mqg_handle** out);
+int32_t ptf_mqg_destroy(ptf_mqg_handle* h);
+const char* ptf_mqg_last_error(const ptf_mqg_handle* h);
+int32_t ptf_mqg_set_q(ptf_mqg_handle* h, const double* q_host);
+int32_t ptf_mqg_set_psi(ptf_mqg_handle* h, const double* psi_host);
+int32_t ptf_mqg_set_sol(ptf_mqg_handle* h, const double* sol_host_interleaved);
+int32_t ptf_mqg_get_sol(ptf_mqg_handle* h, double* sol_host_interleaved);
+int32_t ptf_mqg_updatevars(ptf_mqg_handle* h);
+int32_t ptf_mqg_get_var(ptf_mqg_handle* h, int32_t which /* 0 u, 1 v, 2 q, 3 psi */, double* host);
+int32_t ptf_mqg_get_background(ptf_mqg_handle* h, double* Qx_host, double* Qy_host);
+int32_t ptf_mqg_step(ptf_mqg_handle* h, int64_t nsteps);
+int32_t ptf_mqg_step_until(ptf_mqg_handle* h, double t_stop);
+int32_t ptf_mqg_step_timed(ptf_mqg_handle* h, int64_t nsteps, int32_t with_updatevars, float* device_ms);
+int32_t ptf_mqg_get_clock(const ptf_mqg_handle* h, double* t, int64_t* step, double* dt);
+int32_t ptf_mqg_set_dt(ptf_mqg_handle* h, double dt);
+int32_t ptf_mqg_launch_count(const ptf_mqg_handle* h, int64_t* own_kernels, int64_t* library_calls);
+int32_t ptf_mqg_couple(ptf_mqg_handle* flow, ptf_handle* tracer);
+int32_t ptf_mqg_forget_tracer(ptf_mqg_handle* flow, ptf_handle* tracer);
+int32_t ptf_mqg_step_coupled(ptf_mqg_handle* flow, ptf_handle* tracer, int64_t nsteps, float* device_ms);
+
 #ifdef __cplusplus
 }
 #endif

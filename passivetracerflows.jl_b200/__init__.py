@@ -8,12 +8,13 @@ built library raises — there is no CPU or PyTorch fallback.
 from . import _capi
 from . import parallel
 from . import tracer_advection_diffusion as TracerAdvectionDiffusion
+from . import multilayerqg as MultiLayerQG
 from .tracer_advection_diffusion import (B200, Device, OneDAdvectingFlow, Problem, SeparableFlow,
                                          ThreeDAdvectingFlow, TracerProblem, TwoDAdvectingFlow, gridpoints, noflow,
                                          set_c, step_until, stepforward, updatevars)
 
 __all__ = ["B200", "Device", "Problem", "set_c", "updatevars", "stepforward", "step_until", "OneDAdvectingFlow",
            "TwoDAdvectingFlow", "ThreeDAdvectingFlow", "SeparableFlow", "TracerProblem", "gridpoints", "noflow",
-           "TracerAdvectionDiffusion"]
+           "TracerAdvectionDiffusion", "MultiLayerQG"]
 
 _capi.load()   # fail loudly at import time when the CUDA library is missing

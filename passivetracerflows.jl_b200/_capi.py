@@ -49,6 +49,35 @@ class PtfDesc(C.Structure):
     ]
 
 
+class PtfMqgDesc(C.Structure):
+    """ptf_mqg_desc (include/ptf_b200.h): MultiLayerQG.Problem keyword arguments."""
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("nlayers", C.c_int32),
+        ("nx", C.c_int64),
+        ("ny", C.c_int64),
+        ("Lx", C.c_double),
+        ("Ly", C.c_double),
+        ("f0", C.c_double),
+        ("beta", C.c_double),
+        ("H", C.POINTER(C.c_double)),
+        ("b", C.POINTER(C.c_double)),
+        ("U", C.POINTER(C.c_double)),
+        ("U_is_profile", C.c_int32),
+        ("n_nu", C.c_int32),
+        ("eta", C.POINTER(C.c_double)),
+        ("topographic_pv_gradient", C.c_double * 2),
+        ("mu", C.c_double),
+        ("nu", C.c_double),
+        ("dt", C.c_double),
+        ("stepper", C.c_int32),
+        ("device", C.c_int32),
+        ("aliased_fraction", C.c_double),
+        ("use_graph", C.c_int32),
+        ("reserved", C.c_int32 * 7),
+    ]
+
+
 VELOCITY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
                           C.POINTER(C.c_double))
 COEFF_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.POINTER(C.c_double))
@@ -90,6 +119,27 @@ SIGNATURES = {
     "ptf_device_bytes": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
     "ptf_diag": (C.c_int32, [_H, _DP, _DP, _DP]),
     "ptf_selftest_fft": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _DP, _DP]),
+    # MultiLayerQG flow solver
+    "ptf_mqg_desc_init": (C.c_int32, [C.POINTER(PtfMqgDesc)]),
+    "ptf_mqg_create": (C.c_int32, [C.POINTER(PtfMqgDesc), C.POINTER(_H)]),
+    "ptf_mqg_destroy": (C.c_int32, [_H]),
+    "ptf_mqg_last_error": (C.c_char_p, [_H]),
+    "ptf_mqg_set_q": (C.c_int32, [_H, _DP]),
+    "ptf_mqg_set_psi": (C.c_int32, [_H, _DP]),
+    "ptf_mqg_set_sol": (C.c_int32, [_H, _DP]),
+    "ptf_mqg_get_sol": (C.c_int32, [_H, _DP]),
+    "ptf_mqg_updatevars": (C.c_int32, [_H]),
+    "ptf_mqg_get_var": (C.c_int32, [_H, C.c_int32, _DP]),
+    "ptf_mqg_get_background": (C.c_int32, [_H, _DP, _DP]),
+    "ptf_mqg_step": (C.c_int32, [_H, C.c_int64]),
+    "ptf_mqg_step_until": (C.c_int32, [_H, C.c_double]),
+    "ptf_mqg_step_timed": (C.c_int32, [_H, C.c_int64, C.c_int32, C.POINTER(C.c_float)]),
+    "ptf_mqg_get_clock": (C.c_int32, [_H, _DP, C.POINTER(C.c_int64), _DP]),
+    "ptf_mqg_set_dt": (C.c_int32, [_H, C.c_double]),
+    "ptf_mqg_launch_count": (C.c_int32, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ptf_mqg_couple": (C.c_int32, [_H, _H]),
+    "ptf_mqg_forget_tracer": (C.c_int32, [_H, _H]),
+    "ptf_mqg_step_coupled": (C.c_int32, [_H, _H, C.c_int64, C.POINTER(C.c_float)]),
 }
 
 _lib = None
@@ -127,6 +177,19 @@ def check(status, handle=None):
     generic = lib.ptf_error_string(status).decode()
     if status == EINVAL:
         raise ValueError(f"{generic}: {msg}")   # mirrors the reference's ArgumentError (TAD.jl:234)
+    raise PtfError(status, f"{generic}: {msg}")
+
+
+def check_mqg(status, handle=None):
+    """Same as :func:`check` for MultiLayerQG handles (their message lives in ptf_mqg_last_error)."""
+    if status == OK:
+        return
+    lib = load()
+    msg = lib.ptf_mqg_last_error(handle)
+    msg = msg.decode(errors="replace") if msg else ""
+    generic = lib.ptf_error_string(status).decode()
+    if status == EINVAL:
+        raise ValueError(f"{generic}: {msg}")
     raise PtfError(status, f"{generic}: {msg}")
 
 

@@ -550,6 +550,10 @@ class CufftEngine final : public Engine {
   }
   void set_velocity_coeffs(int comp, int nterms, const double* a) override { vs.set_coeffs(comp, nterms, a); }
   void set_layered_shift(const double* U) override { vs.set_shift(U); sync_vel(); }
+  void set_velocity_external(int comp, const double* dev, int64_t count) override {
+    vs.set_external(comp, dev, count);
+    sync_vel();
+  }
 
   // ---------------- state ----------------
   void set_c(const double* c_host, bool replicate) override {
@@ -681,6 +685,9 @@ class CufftEngine final : public Engine {
     pt.begin(4);
     int64_t half = g.lpts() / 2;
     VelArgs va = vs.va;
+    if (va.kind != PTF_FLOW_SEPARABLE)
+      for (int c = 0; c < nd; ++c)
+        if (!va.arr[c]) throw Error(PTF_EINVAL, "velocity fields have not been set (ptf_set_velocity / callback)");
     if (g.slab)
       for (int c = 0; c < 3; ++c)
         if (va.sep[c].zt) va.sep[c].zt += g.zoff;  // separable z tables are global: start at this rank's first plane

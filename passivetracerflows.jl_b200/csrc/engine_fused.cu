@@ -119,6 +119,10 @@ class FusedEngine final : public Engine {
   }
   void set_velocity_coeffs(int comp, int nterms, const double* a) override { vs.set_coeffs(comp, nterms, a); }
   void set_layered_shift(const double* U) override { vs.set_shift(U); sync_vel(); }
+  void set_velocity_external(int comp, const double* dev, int64_t count) override {
+    vs.set_external(comp, dev, count);
+    sync_vel();
+  }
 
   // ---------------- layout changes at the boundary ----------------
   void transpose(const double2* in, double2* out, int R, int Cc, double scale) {

@@ -226,6 +226,13 @@ void build_context(ptf_handle* h, const ptf_desc* d) {
     ax.ay_hi = hi(g.ny);
     ax.az_lo = lo(g.nz);
     ax.az_hi = hi(g.nz);
+    if (a <= 0.0) {  // FF: kalias = nk/2 + 1, kralias = nkr — aliased_fraction = 0 still zeroes the Nyquist index
+      ax.ax_lo = g.nx / 2;
+      ax.ay_lo = g.ny / 2;
+      ax.ay_hi = g.ny / 2 + 1;
+      ax.az_lo = g.nz / 2;
+      ax.az_hi = g.nz / 2 + 1;
+    }
   }
 }
 
@@ -272,6 +279,42 @@ void do_steps(ptf_handle* h, int64_t nsteps) {
 }
 
 }  // namespace
+
+// ---- hooks used by the MultiLayerQG coupling (engine_mqg.cu) ----
+namespace ptf {
+void couple_layered_velocity(ptf_handle* h, const double* u_dev, const double* v_dev, const double* U_host,
+                             int64_t count) {
+  PTF_CUDA(cudaStreamSynchronize(h->ctx.stream));
+  h->engine->set_velocity_external(0, u_dev, count);
+  h->engine->set_velocity_external(1, v_dev, count);
+  h->engine->set_layered_shift(U_host);   // MQGprob.params.U, added to u in the product (TAD.jl:795)
+}
+void decouple_layered_velocity(ptf_handle* h) {
+  cudaSetDevice(h->ctx.device);
+  cudaStreamSynchronize(h->ctx.stream);
+  try {
+    h->engine->set_velocity_external(0, nullptr, 0);
+    h->engine->set_velocity_external(1, nullptr, 0);
+  } catch (...) {
+  }
+}
+cudaStream_t tracer_stream(ptf_handle* h) { return h->ctx.stream; }
+int tracer_device(ptf_handle* h) { return h->ctx.device; }
+void tracer_geometry(ptf_handle* h, int64_t* nx, int64_t* ny, int64_t* nbatch, double* Lx, double* Ly, double* dt,
+                     int* flow_kind, int* ndim) {
+  const Geometry& g = h->ctx.g;
+  *nx = g.nx;
+  *ny = g.ny;
+  *nbatch = g.B;
+  *Lx = g.Lx;
+  *Ly = g.Ly;
+  *dt = h->ctx.dt;
+  *flow_kind = h->ctx.d.flow_kind;
+  *ndim = g.ndim;
+}
+void tracer_step_one(ptf_handle* h) { do_steps(h, 1); }
+void tracer_set_mqg(ptf_handle* h, ptf_mqg_handle* m) { h->mqg = m; }
+}  // namespace ptf
 
 extern "C" {
 
@@ -387,6 +430,8 @@ int32_t ptf_destroy(ptf_handle* h) {
   if (!h) return PTF_OK;
   cudaSetDevice(h->ctx.device);
   if (h->ctx.stream) cudaStreamSynchronize(h->ctx.stream);
+  if (h->mqg) ptf_mqg_forget_tracer(h->mqg, h);   // the coupled flow keeps running on this (soon destroyed) stream: see
+                                                  // ptf_mqg_forget_tracer, which moves it back to its own stream
   h->engine.reset();
   for (auto& p : h->pinned_vel)
     if (p) cudaFreeHost(p);

@@ -130,6 +130,10 @@ class Engine {
                                       const double* coeff0) = 0;
   virtual void set_velocity_coeffs(int comp, int nterms, const double* a) = 0;
   virtual void set_layered_shift(const double* U) = 0;  // U(y, layer) added to u; nullptr = none
+  virtual void set_velocity_external(int comp, const double* dev, int64_t count) {  // alias a device field
+    (void)comp; (void)dev; (void)count;
+    throw Error(PTF_EUNSUPPORTED, "this engine cannot read device-resident velocity fields");
+  }
   virtual void set_c(const double* c_host, bool replicate) = 0;
   virtual void get_c(double* c_host) = 0;
   virtual void set_sol(const double* s_host) = 0;
@@ -171,8 +175,10 @@ bool fused1d_engine_supports(const Context& ctx, std::string* why);
 
 }  // namespace ptf
 
+struct ptf_mqg_handle;
 struct ptf_handle {
   ptf::Context ctx;
+  ptf_mqg_handle* mqg = nullptr;  // coupled MultiLayerQG flow (ptf_mqg_couple), not owned
   std::unique_ptr<ptf::Engine> engine;
   std::string last_error;
   ptf_velocity_fn vel_fn = nullptr;

@@ -72,6 +72,18 @@ struct VelocityStore {
     PTF_CUDA(cudaStreamSynchronize(stream));
   }
 
+  // Alias a device-resident field owned by someone else (the coupled MultiLayerQG solver's vars.u / vars.v, TAD.jl:795-796).
+  // nullptr detaches.  Everything that reads it must be ordered on the same stream as its producer.
+  void set_external(int comp, const double* dev, int64_t count) {
+    PTF_REQUIRE(comp >= 0 && comp < g->ndim, "velocity component out of range");
+    PTF_REQUIRE(dev == nullptr || count == g->lpts() * g->B, "external velocity must hold one field per member");
+    vel[comp].release();
+    if (va.arr[comp] != dev) dirty = true;
+    va.arr[comp] = dev;
+    if (va.member_stride != g->lpts()) dirty = true;
+    va.member_stride = g->lpts();
+  }
+
   void set_separable(int comp, int nterms, const double* xt, const double* yt, const double* zt,
                      const double* coeff0) {
     const int nd = g->ndim;

@@ -250,6 +250,7 @@ class TracerProblem:
         self._keep = []          # ctypes callbacks must outlive the handle
         self._vel_funcs = None
         self._mqg = None
+        self._mqg_on_device = False
 
     # ---- lifetime ----
     def close(self):
@@ -365,7 +366,7 @@ class TracerProblem:
 
     def _refresh_mqg_velocity(self):
         q = self._mqg
-        if q is None:
+        if q is None or self._mqg_on_device:   # device-coupled flows are read in place (ptf_mqg_couple)
             return
         self.set_layered_velocity(q.vars.u, q.vars.v, getattr(q.params, "U", None))
 
@@ -494,6 +495,8 @@ def _layered_problem(MQGprob, *, kappa, eta, stepper, tracer_release_time, dev):
     ``params.nlayers``, and the verbs ``step_until(t)`` / ``updatevars()``.
     """
     g = MQGprob.grid
+    if getattr(MQGprob, "dev", None) is not None and isinstance(MQGprob.dev, B200):
+        dev = B200(device=MQGprob.dev.device, engine=dev.engine, use_graph=dev.use_graph)   # same device as the flow
     if tracer_release_time < 0:
         raise ValueError("tracer_release_time must be non-negative!")      # ArgumentError, TAD.jl:234
     if tracer_release_time > 0:
@@ -507,7 +510,13 @@ def _layered_problem(MQGprob, *, kappa, eta, stepper, tracer_release_time, dev):
     prob = TracerProblem(dev, grid, params, MQGprob.clock.dt, stepper, _capi.FLOW_LAYERED, nbatch=nlayers,
                          velocity_per_batch=True)
     prob._mqg = MQGprob
-    prob._refresh_mqg_velocity()
+    from . import multilayerqg
+    if isinstance(MQGprob, multilayerqg.MultiLayerQGProblem):
+        # flow solver lives on the same device: alias its u, v buffers instead of uploading every step
+        multilayerqg.couple(prob, MQGprob)
+        prob._mqg_on_device = True
+    else:
+        prob._refresh_mqg_velocity()
     return prob
 
 
