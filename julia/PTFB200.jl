@@ -128,4 +128,101 @@ function step_until!(p::Prob, stop_time)
   sync_clock!(p)
 end
 
+# ------------------------------------------------------------------------------------------------------------
+# MultiLayerQG flow on the device (ptf_mqg_* in include/ptf_b200.h): the calls the reference makes into
+# GeophysicalFlows.MultiLayerQG — examples/turbulent_advection-diffusion.jl:56-69,149-151; TAD.jl:225-250,488,795-796
+# ------------------------------------------------------------------------------------------------------------
+mutable struct PtfMqgDesc
+  struct_size::UInt32; nlayers::Int32
+  nx::Int64; ny::Int64
+  Lx::Float64; Ly::Float64; f0::Float64; beta::Float64
+  H::Ptr{Float64}; b::Ptr{Float64}; U::Ptr{Float64}
+  U_is_profile::Int32; n_nu::Int32
+  eta::Ptr{Float64}
+  topographic_pv_gradient::NTuple{2,Float64}
+  mu::Float64; nu::Float64; dt::Float64
+  stepper::Int32; device::Int32
+  aliased_fraction::Float64
+  use_graph::Int32; reserved::NTuple{7,Int32}
+  PtfMqgDesc() = new()
+end
+
+mutable struct MQGProb
+  h::Ptr{Cvoid}; nlayers::Int; nx::Int; ny::Int; clock::Clock; U::Vector{Float64}
+end
+
+checkmqg(status::Int32, h=C_NULL) = status == 0 ? nothing :
+  (msg = unsafe_string(ccall((:ptf_mqg_last_error, LIB), Cstring, (Ptr{Cvoid},), h));
+   status == 1 ? throw(ArgumentError(msg)) : error("libptf_b200 status $status: $msg"))
+
+"MultiLayerQG.Problem(nlayers, B200(); nx, Lx, f₀, H, b, U, μ, β, dt, stepper, aliased_fraction) — examples/…:56-58"
+function MultiLayerQGProblem(nlayers::Int, dev::B200; nx=128, ny=nx, Lx=2π, Ly=Lx, f₀=1.0, β=0.0, U=zeros(nlayers),
+                             H=fill(1/nlayers, nlayers), b=-(1 .+ (0:nlayers-1)/nlayers), μ=0.0, ν=0.0, nν=1,
+                             dt=0.01, stepper="RK4", aliased_fraction=1/3)
+  d = PtfMqgDesc(); ccall((:ptf_mqg_desc_init, LIB), Int32, (Ref{PtfMqgDesc},), d)
+  Hv, bv, Uv = Float64.(collect(H)), Float64.(collect(b)), Float64.(collect(U))
+  d.nlayers, d.nx, d.ny, d.Lx, d.Ly, d.f0, d.beta = nlayers, nx, ny, Lx, Ly, f₀, β
+  d.mu, d.nu, d.n_nu, d.dt, d.aliased_fraction, d.device = μ, ν, nν, dt, aliased_fraction, dev.device
+  filt = startswith(stepper, "Filtered")
+  d.stepper = STEPPERS[filt ? stepper[9:end] : stepper] | (filt ? 16 : 0)
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  GC.@preserve Hv bv Uv begin
+    d.H, d.b, d.U = pointer(Hv), pointer(bv), pointer(Uv)       # copied by the library before ptf_mqg_create returns
+    checkmqg(ccall((:ptf_mqg_create, LIB), Int32, (Ref{PtfMqgDesc}, Ref{Ptr{Cvoid}}), d, h))
+  end
+  p = MQGProb(h[], nlayers, nx, ny, Clock(dt, 0.0, 0), Uv)
+  finalizer(q -> ccall((:ptf_mqg_destroy, LIB), Int32, (Ptr{Cvoid},), q.h), p)
+  return p
+end
+
+"MultiLayerQG.set_q!(MQGprob, q) — examples/…:69"
+set_q!(p::MQGProb, q::Array{Float64,3}) =
+  GC.@preserve q checkmqg(ccall((:ptf_mqg_set_q, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), p.h, q), p.h)
+
+"MultiLayerQG.updatevars!(MQGprob) — TAD.jl:488, examples/…:151 (device side; read fields with mqg_var)"
+updatevars!(p::MQGProb) = checkmqg(ccall((:ptf_mqg_updatevars, LIB), Int32, (Ptr{Cvoid},), p.h), p.h)
+
+"MQGprob.vars.u / .v / .q / .ψ as of the last updatevars! (which = 0, 1, 2, 3)"
+function mqg_var(p::MQGProb, which::Integer)
+  out = Array{Float64}(undef, p.nx, p.ny, p.nlayers)
+  checkmqg(ccall((:ptf_mqg_get_var, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), p.h, which, out), p.h)
+  return out
+end
+
+function sync_clock!(p::MQGProb)
+  t = Ref(0.0); s = Ref(Int64(0)); dt = Ref(0.0)
+  ccall((:ptf_mqg_get_clock, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}, Ref{Int64}, Ref{Float64}), p.h, t, s, dt)
+  p.clock.t, p.clock.step, p.clock.dt = t[], s[], dt[]
+end
+
+"stepforward!(MQGprob[, nsteps]) — examples/…:150"
+function stepforward!(p::MQGProb, nsteps::Integer=1)
+  checkmqg(ccall((:ptf_mqg_step, LIB), Int32, (Ptr{Cvoid}, Int64), p.h, nsteps), p.h); sync_clock!(p)
+end
+
+"step_until!(MQGprob, t) — TAD.jl:238"
+function step_until!(p::MQGProb, t)
+  checkmqg(ccall((:ptf_mqg_step_until, LIB), Int32, (Ptr{Cvoid}, Float64), p.h, t), p.h); sync_clock!(p)
+end
+
+"""
+Problem(MQGprob; κ, η, stepper, tracer_release_time) — TAD.jl:225-250.  `tracer` is the layered tracer problem created
+with nbatch = nlayers and PTF_FLOW_LAYERED; after this call its calcN! reads MQGprob.vars.u .+ params.U and vars.v
+(TAD.jl:795-796) directly from the flow solver's device buffers.
+"""
+function couple!(tracer::Prob, flow::MQGProb; tracer_release_time=0)
+  tracer_release_time < 0 && throw(ArgumentError("tracer_release_time must be non-negative!"))   # TAD.jl:234
+  tracer_release_time > 0 && step_until!(flow, tracer_release_time)                                # TAD.jl:236-239
+  checkmqg(ccall((:ptf_mqg_couple, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), flow.h, tracer.h), flow.h)
+end
+
+"the loop body of examples/…:149-151, nsteps times, without host round trips; returns device milliseconds"
+function step_coupled!(tracer::Prob, flow::MQGProb, nsteps::Integer=1)
+  ms = Ref(Float32(0))
+  checkmqg(ccall((:ptf_mqg_step_coupled, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{Float32}),
+                 flow.h, tracer.h, nsteps, ms), flow.h)
+  sync_clock!(tracer); sync_clock!(flow)
+  return ms[]
+end
+
 end # module
