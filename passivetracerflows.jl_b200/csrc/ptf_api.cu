@@ -157,14 +157,35 @@ void build_context(ptf_handle* h, const ptf_desc* d) {
       PTF_REQUIRE(d->nbatch % d->nranks == 0, "nbatch must be divisible by nranks for PTF_DECOMP_BATCH");
       g.B = d->nbatch / d->nranks;
       g.Boffset = g.B * d->rank;
+    } else if (d->decomposition == PTF_DECOMP_SLAB && d->ndim == 2) {
+      PTF_REQUIRE(d->nbatch == 1, "slab decomposition needs nbatch == 1");
+      PTF_REQUIRE(g.ny % d->nranks == 0, "ny must be divisible by nranks");
+      PTF_REQUIRE(d->flow_kind != PTF_FLOW_LAYERED, "layered flows are not slab-decomposed (use PTF_DECOMP_BATCH)");
+      g.slab2d = true;
+      g.P = d->nranks;
+      g.rank = d->rank;
     } else if (d->decomposition == PTF_DECOMP_SLAB) {
-      PTF_REQUIRE(d->ndim == 3, "slab decomposition is implemented for 3-D problems");
+      PTF_REQUIRE(d->ndim == 3, "slab decomposition is implemented for 2-D and 3-D problems");
       PTF_REQUIRE(d->nbatch == 1, "slab decomposition needs nbatch == 1");
       PTF_REQUIRE(g.ny % d->nranks == 0 && g.nz % d->nranks == 0, "ny and nz must be divisible by nranks");
       g.slab = true;
       g.P = d->nranks;
       g.rank = d->rank;
     }  // PTF_DECOMP_NONE: independent replicas
+  }
+  // single-process test hook: run the 2-D slab engine with P = 1 (every kernel but the NCCL exchange)
+  if (!g.slab2d && d->nranks == 1 && d->ndim == 2 && d->nbatch == 1 && d->decomposition == PTF_DECOMP_SLAB &&
+      d->flow_kind != PTF_FLOW_LAYERED) {
+    g.slab2d = true;
+    g.P = 1;
+    g.rank = 0;
+  }
+  if (g.slab2d) {
+    g.nyp = g.ny / g.P;
+    g.ypoff = g.nyp * g.rank;
+    g.kc = (g.nkr + g.P - 1) / g.P;
+    g.koff = g.kc * g.rank;
+    g.kvalid = std::max<int64_t>(0, std::min<int64_t>(g.kc, g.nkr - g.koff));
   }
   g.nzl = g.slab ? g.nz / g.P : g.nz;
   g.nyl = g.slab ? g.ny / g.P : g.ny;
@@ -189,7 +210,7 @@ void build_context(ptf_handle* h, const ptf_desc* d) {
   c.t = 0.0;
   c.step = 0;
 
-  if (g.slab) {
+  if (g.slab || (g.slab2d && g.P > 1)) {
 #ifdef PTF_WITH_NCCL
     c.nccl_comm = acquire_comm(d->nccl_id, d->nranks, d->rank);
 #else
@@ -399,7 +420,10 @@ int32_t ptf_create(const ptf_desc* d, ptf_handle** out) {
     std::string why;
     int want = d->engine;
     const bool one_d = h->ctx.g.ndim == 1;
-    if (want == PTF_ENGINE_FUSED) {
+    if (h->ctx.g.slab2d) {
+      if (want == PTF_ENGINE_FUSED) throw Error(PTF_EUNSUPPORTED, "fused engine: 2-D slab decomposition runs on the cuFFT pipeline");
+      h->engine = make_slab2d_engine(h->ctx);
+    } else if (want == PTF_ENGINE_FUSED) {
       if (one_d) {
         if (!fused1d_engine_supports(h->ctx, &why)) throw Error(PTF_EUNSUPPORTED, "fused engine: " + why);
         h->engine = make_fused1d_engine(h->ctx);
@@ -453,6 +477,12 @@ int32_t ptf_local_shape(const ptf_handle* h, int64_t phys_n[4], int64_t spec_n[4
   if (spec_n) { spec_n[0] = g.nkr; spec_n[1] = g.nyl; spec_n[2] = g.nz; spec_n[3] = g.B; }
   if (phys_offset) { phys_offset[0] = phys_offset[1] = 0; phys_offset[2] = g.zoff; phys_offset[3] = g.Boffset; }
   if (spec_offset) { spec_offset[0] = 0; spec_offset[1] = g.yoff; spec_offset[2] = 0; spec_offset[3] = g.Boffset; }
+  if (g.slab2d) {  // physical rows [ypoff, ypoff+nyp); spectral columns kr in [koff, koff+kvalid), all ky
+    if (phys_n) phys_n[1] = g.nyp;
+    if (phys_offset) phys_offset[1] = g.ypoff;
+    if (spec_n) { spec_n[0] = g.kvalid; spec_n[1] = g.ny; }
+    if (spec_offset) { spec_offset[0] = g.koff; spec_offset[1] = 0; }
+  }
   return PTF_OK;
 }
 

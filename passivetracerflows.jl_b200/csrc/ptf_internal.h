@@ -81,8 +81,12 @@ struct Geometry {
   bool slab = false;
   int P = 1, rank = 0;
   int64_t nzl = 1, nyl = 1, zoff = 0, yoff = 0;
-  int64_t lpts() const { return nx * ny * nzl; }    // local real points per member
-  int64_t lspec() const { return nkr * nyl * nz; }  // local complex coefficients per member
+  // 2-D slab decomposition (engine_slab2d.cu): physical rows [ypoff, ypoff+nyp), spectral columns kr in
+  // [koff, koff+kvalid) stored in kc = ceil(nkr/P) padded columns
+  bool slab2d = false;
+  int64_t nyp = 1, ypoff = 0, kc = 1, koff = 0, kvalid = 1;
+  int64_t lpts() const { return slab2d ? nx * nyp : nx * ny * nzl; }       // local real points per member
+  int64_t lspec() const { return slab2d ? kvalid * ny : nkr * nyl * nz; }  // local complex coefficients per member
   std::vector<double> kx, ky, kz;                 // wavenumbers (kz/ky size 1 == {0} on unused axes)
 };
 
@@ -170,6 +174,7 @@ std::unique_ptr<Engine> make_cufft_engine(Context& ctx);
 std::unique_ptr<Engine> make_fused_engine(Context& ctx);  // throws PTF_EUNSUPPORTED when the grid does not qualify
 bool fused_engine_supports(const Context& ctx, std::string* why);
 void selftest_fft(int n, int dir, int count, const double* in_host, double* out_host);
+std::unique_ptr<Engine> make_slab2d_engine(Context& ctx);
 std::unique_ptr<Engine> make_fused1d_engine(Context& ctx);
 bool fused1d_engine_supports(const Context& ctx, std::string* why);
 

@@ -241,6 +241,10 @@ class TracerProblem:
         # ky-rows [ky_offset, ky_offset+ny_local) in spectral space
         self.nz_local, self.z_offset = int(pn[2]), int(po[2])
         self.ny_local, self.ky_offset = int(sn[1]), int(so[1])
+        # 2-D slab decomposition: rows [y_offset, y_offset+ny_phys_local) in physical space and kr-columns
+        # [kr_offset, kr_offset+nkr_local) (all ky) in spectral space
+        self.ny_phys_local, self.y_offset = int(pn[1]), int(po[1])
+        self.nkr_local, self.kr_offset = int(sn[0]), int(so[0])
         nd = grid.ndim
         lead = (self.local_nbatch,) if self.nbatch > 1 else ()
         self._pshape = lead + tuple(int(pn[a]) for a in reversed(range(nd)))
@@ -303,6 +307,9 @@ class TracerProblem:
         pts = pts if isinstance(pts, tuple) else (pts,)
         if self.grid.ndim == 3 and self.nz_local != self.grid.nz:
             sl = slice(self.z_offset, self.z_offset + self.nz_local)
+            pts = tuple(p[sl] for p in pts)
+        if self.grid.ndim == 2 and self.ny_phys_local != self.grid.ny:
+            sl = slice(self.y_offset, self.y_offset + self.ny_phys_local)
             pts = tuple(p[sl] for p in pts)
         return pts
 

@@ -84,3 +84,60 @@ def test_slab_extents():
     assert slab_extents(1024, 8, 3) == (128, 384)
     with pytest.raises(ValueError):
         slab_extents(10, 4, 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2-D slab scheme (csrc/engine_slab2d.cu): physical rows sharded, spectral kr-columns sharded in kc = ceil(nkr/P) padded
+# columns, spectral layout [kc][ny].  Same pack / exchange / unpack formulas as the kernels k2_pack_rows, k2_unpack_rows
+# and the two transposes, with NumPy FFTs standing in for the local cuFFT batches.
+# ---------------------------------------------------------------------------------------------------------------------
+def _worker2d(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nx, ny = n
+    nkr = nx // 2 + 1
+    nyp = ny // world
+    kc = -(-nkr // world)
+    koff = rank * kc
+    kvalid = max(0, min(kc, nkr - koff))
+    rng = np.random.default_rng(5)
+    c = rng.standard_normal((ny, nx))
+    ref = np.fft.rfft2(c)                                                  # [ny][nkr]
+    rows = np.fft.rfft(c[rank * nyp:(rank + 1) * nyp], axis=1)             # local 1-D r2c: [nyp][nkr]
+    # k2_pack_rows: blocks[d][jl][cc] = rows[jl][d*kc + cc] (zero beyond nkr)
+    blocks = np.zeros((world, nyp, kc), dtype=np.complex128)
+    for d in range(world):
+        w = max(0, min(kc, nkr - d * kc))
+        blocks[d, :, :w] = rows[:, d * kc:d * kc + w]
+    recv = _a2a(blocks)                                                    # [src][nyp][kc] == [ny][kc]
+    spec = np.fft.fft(recv.reshape(ny, kc).T, axis=1)                      # transpose -> [kc][ny], c2c along y
+    e_f = np.abs(spec[:kvalid] - ref[:, koff:koff + kvalid].T).max() / np.abs(ref).max()
+    e_pad = np.abs(spec[kvalid:]).max() if kvalid < kc else 0.0            # padded columns stay exactly zero
+    # inverse: c2c along y -> transpose ([ny][kc]: block d = rows of rank d) -> all-to-all -> k2_unpack_rows -> c2r along x
+    s = np.fft.ifft(spec, axis=1) * ny
+    recv = _a2a(np.ascontiguousarray(s.T).reshape(world, nyp, kc))
+    rows2 = np.empty((nyp, nkr), dtype=np.complex128)
+    for k in range(nkr):
+        rows2[:, k] = recv[k // kc, :, k % kc]
+    back = np.fft.irfft(rows2, n=nx, axis=1) / ny
+    e_i = np.abs(back - c[rank * nyp:(rank + 1) * nyp]).max()
+    q.put((rank, float(e_f), float(e_i), float(e_pad)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [(16, 8), (10, 12), (6, 4)])
+def test_slab2d_transpose_scheme_world2(n):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker2d, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, e_f, e_i, e_pad in res:
+        assert e_f < 1e-13 and e_i < 1e-13 and e_pad == 0.0, (rank, e_f, e_i, e_pad)
