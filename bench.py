@@ -236,6 +236,58 @@ def run_slab3d(args, rank, world, local_rank, P, dist, barrier, max_over_ranks):
         print(json.dumps(line), flush=True)
 
 
+def run_slab2d(args, rank, world, local_rank, P, dist, barrier, max_over_ranks):
+    """One large 2-D cellular-flow problem (BASELINE configs[1] scaled up) slab-decomposed over the GPUs: physical rows
+    sharded, spectral kr-columns sharded, one NCCL all-to-all per transform.  Strong scaling."""
+    n = args.n2
+    kappa = 0.1
+    dt = 0.5 * 2.785 / (kappa * 2 * (n / 2) ** 2)
+    flow = P.SeparableFlow(terms=[[(np.cos, np.sin)], [(np.sin, np.cos)]],
+                           coeffs=lambda t, a: [0.2 if a == 0 else -0.2], steadyflow=True)   # cellular flow, in registers
+    dev = P.parallel.init_b200("slab", device=local_rank) if world > 1 else P.B200(device=local_rank, decomposition="slab")
+    prob = P.Problem(dev, flow, nx=n, kappa=kappa, dt=dt, stepper=args.stepper)
+    x = prob.grid.x
+    ys = x[prob.y_offset:prob.y_offset + prob.ny_phys_local]
+    c0 = 0.5 * np.exp(-((x[None, :] - 0.4 * np.pi) ** 2 + ys[:, None] ** 2) / (2 * 0.15 ** 2))
+    prob.set_c(np.ascontiguousarray(c0))
+    for _ in range(args.warmup):
+        prob.stepforward(1)
+    own0, lib0 = prob.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_ms = prob.step_timed(args.steps)
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join()
+    own1, lib1 = prob.launch_count()
+    dev_ms = max_over_ranks(dev_ms)
+    npts = n * n
+    value = npts * args.steps / (dev_ms * 1e-3)
+    d = prob.diagnostics()
+    peak, peak_src = peaks()
+    balg = b_alg(2, args.stepper) - 32 * 2      # velocities generated in registers (SURVEY 8d)
+    step_ms = dev_ms / args.steps
+    spec_local = (n // 2 + 1) * n * 16 / world
+    a2a_bytes = 12 * spec_local * (world - 1) / world if world > 1 else 0     # 3 exchanged fields per stage
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"slab2d_{n}^2_{args.stepper}_cellular_flow (BASELINE configs[1] beyond one fused-engine grid)",
+                           "n": n, "stepper": args.stepper, "dt": dt, "engine": "slab2d (cuFFT batches + own kernels)",
+                           "decomposition": "y-rows (physical) / kr-columns (spectral), NCCL all-to-all per transform",
+                           "state_finite": bool(np.isfinite(d["max_abs_sol"])), "l2": "fields larger than L2"},
+                "gpu_launches": own1 - own0, "library_calls": lib1 - lib0,
+                "step_roofline": {"b_alg_bytes_per_point_step": balg, "achieved": balg * npts / (step_ms * 1e-3) / 1e9,
+                                  "peak": peak * world, "unit": "GB/s",
+                                  "frac": balg * npts / (step_ms * 1e-3) / 1e9 / (peak * world)},
+                "nvlink": {"alltoall_bytes_out_per_gpu_per_step": a2a_bytes,
+                           "floor_ms_per_step_at_770GBs": a2a_bytes / 770e9 * 1e3},
+                "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,10 +298,11 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "cufft", "fused"])
     ap.add_argument("--stepper", default="RK4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cellular2d", choices=["cellular2d", "slab3d"],
+    ap.add_argument("--workload", default="cellular2d", choices=["cellular2d", "slab3d", "slab2d"],
                     help="cellular2d: BASELINE configs[1], one problem per GPU (default, the graded line); "
                          "slab3d: BASELINE configs[3], ONE n^3 problem slab-decomposed over all GPUs (strong scaling)")
     ap.add_argument("--n3", type=int, default=512, help="grid size of the slab3d workload (n^3)")
+    ap.add_argument("--n2", type=int, default=16384, help="grid size of the slab2d workload (n^2)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -292,6 +345,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if args.workload == "slab2d":
+        run_slab2d(args, rank, world, local_rank, P, dist, barrier, max_over_ranks)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     if args.workload == "slab3d":
         run_slab3d(args, rank, world, local_rank, P, dist, barrier, max_over_ranks)
         if dist is not None:
