@@ -19,6 +19,7 @@
  *   ptf_set_velocity_callback   the u(x,y,t) closures of ConstDiffTimeVaryingFlowParams TAD.jl:268-348,
  *                          evaluated at clock.t once per step (TAD.jl:701,718,737)
  *   ptf_set_velocity_separable  same closures, for flows of the form sum_m a_m(t) X_m(x) Y_m(y) Z_m(z)
+ *   ptf_set_velocity_expr  same closures, written as CUDA expressions and compiled at run time (NVRTC)
  *   ptf_set_layered_velocity    MQGprob.vars.u .+ MQGprob.params.U, MQGprob.vars.v  TAD.jl:795-796
  *   ptf_set_c              set_c!(prob, c)        TAD.jl:844-872
  *   ptf_get_c              updatevars!(prob) + read of prob.vars.c   TAD.jl:815-837
@@ -73,7 +74,9 @@ enum {
   PTF_FLOW_STEADY = 0,    /* arrays uploaded once with ptf_set_velocity (AbstractSteadyFlowParams) */
   PTF_FLOW_CALLBACK = 1,  /* host callback fills u,v,w at clock.t once per step (AbstractTimeVaryingFlowParams) */
   PTF_FLOW_SEPARABLE = 2, /* sum_m a_m(t) X_m(x) Y_m(y) Z_m(z); coefficient callback per step; zero HBM bytes */
-  PTF_FLOW_LAYERED = 3    /* per-layer u,v (+U(y,layer)) re-supplied by the caller between steps (MQG coupling) */
+  PTF_FLOW_LAYERED = 3,   /* per-layer u,v (+U(y,layer)) re-supplied by the caller between steps (MQG coupling) */
+  PTF_FLOW_EXPR = 4       /* u,v,w given as CUDA expressions in (x,y,z,t), compiled at run time into the product kernel and
+                             evaluated in registers at clock.t: zero HBM bytes, no per-step upload (cuFFT pipelines only) */
 };
 
 /* which implementation executes the step */
@@ -150,6 +153,11 @@ int32_t ptf_set_velocity_callback(ptf_handle* h, ptf_velocity_fn fn, void* user)
 int32_t ptf_set_velocity_separable(ptf_handle* h, int32_t comp, int32_t nterms, const double* xtab,
                                    const double* ytab, const double* ztab, const double* coeff0);
 int32_t ptf_set_coeff_callback(ptf_handle* h, ptf_coeff_fn fn, void* user);
+/* PTF_FLOW_EXPR: component `comp` as a C expression in the doubles x, y, z, t (CUDA device math: sin, cos, exp, ...; `pi`),
+ * e.g. "(sin(z) + cos(y)) * (1 + 0.5*sin(t))".  The same closures the reference keeps in ConstDiffTimeVaryingFlowParams
+ * (TAD.jl:268-348) and evaluates at clock.t on gridpoints(grid) (TAD.jl:715-718).  Compiled when the last component is
+ * set; a compile error returns PTF_EINVAL with the compiler log in ptf_last_error. */
+int32_t ptf_set_velocity_expr(ptf_handle* h, int32_t comp, const char* expr);
 int32_t ptf_set_layered_velocity(ptf_handle* h, const double* u, const double* v, const double* U);
 
 /* state */

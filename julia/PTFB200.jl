@@ -128,6 +128,14 @@ function step_until!(p::Prob, stop_time)
   sync_clock!(p)
 end
 
+"""
+Time-varying flow given as CUDA expressions in x, y, z, t (PTF_FLOW_EXPR = 4 in `d.flow_kind` at creation): the closures of
+ConstDiffTimeVaryingFlowParams (TAD.jl:268-348) evaluated at clock.t in registers, e.g.
+`set_velocity_expr!(prob, 0, "(sin(z) + cos(y)) * (1 + 0.5*sin(t))")`.  A syntax error throws ArgumentError with the log.
+"""
+set_velocity_expr!(p::Prob, comp::Integer, expr::AbstractString) =
+  check(ccall((:ptf_set_velocity_expr, LIB), Int32, (Ptr{Cvoid}, Int32, Cstring), p.h, comp, expr), p.h)
+
 # ------------------------------------------------------------------------------------------------------------
 # MultiLayerQG flow on the device (ptf_mqg_* in include/ptf_b200.h): the calls the reference makes into
 # GeophysicalFlows.MultiLayerQG — examples/turbulent_advection-diffusion.jl:56-69,149-151; TAD.jl:225-250,488,795-796

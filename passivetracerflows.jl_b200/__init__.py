@@ -9,12 +9,12 @@ from . import _capi
 from . import parallel
 from . import tracer_advection_diffusion as TracerAdvectionDiffusion
 from . import multilayerqg as MultiLayerQG
-from .tracer_advection_diffusion import (B200, Device, OneDAdvectingFlow, Problem, SeparableFlow,
+from .tracer_advection_diffusion import (B200, Device, ExpressionFlow, OneDAdvectingFlow, Problem, SeparableFlow,
                                          ThreeDAdvectingFlow, TracerProblem, TwoDAdvectingFlow, gridpoints, noflow,
                                          set_c, step_until, stepforward, updatevars)
 
 __all__ = ["B200", "Device", "Problem", "set_c", "updatevars", "stepforward", "step_until", "OneDAdvectingFlow",
-           "TwoDAdvectingFlow", "ThreeDAdvectingFlow", "SeparableFlow", "TracerProblem", "gridpoints", "noflow",
+           "TwoDAdvectingFlow", "ThreeDAdvectingFlow", "SeparableFlow", "ExpressionFlow", "TracerProblem", "gridpoints", "noflow",
            "TracerAdvectionDiffusion", "MultiLayerQG"]
 
 _capi.load()   # fail loudly at import time when the CUDA library is missing

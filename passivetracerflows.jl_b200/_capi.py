@@ -11,7 +11,7 @@ OK, EINVAL, ECUDA, ECUFFT, ENCCL, ENOMEM, EUNSUPPORTED, ENODEVICE = range(8)
 
 STEPPER_IDS = {"ForwardEuler": 0, "RK4": 1, "ETDRK4": 2, "LSRK54": 3, "AB3": 4}
 STEPPER_FILTERED = 16
-FLOW_STEADY, FLOW_CALLBACK, FLOW_SEPARABLE, FLOW_LAYERED = 0, 1, 2, 3
+FLOW_STEADY, FLOW_CALLBACK, FLOW_SEPARABLE, FLOW_LAYERED, FLOW_EXPR = 0, 1, 2, 3, 4
 ENGINE_AUTO, ENGINE_CUFFT, ENGINE_FUSED = 0, 1, 2
 ENGINE_NAMES = {"auto": ENGINE_AUTO, "cufft": ENGINE_CUFFT, "fused": ENGINE_FUSED}
 DECOMP_NONE, DECOMP_BATCH, DECOMP_SLAB = 0, 1, 2
@@ -101,6 +101,7 @@ SIGNATURES = {
     "ptf_set_velocity_callback": (C.c_int32, [_H, VELOCITY_FN, C.c_void_p]),
     "ptf_set_velocity_separable": (C.c_int32, [_H, C.c_int32, C.c_int32, _DP, _DP, _DP, _DP]),
     "ptf_set_coeff_callback": (C.c_int32, [_H, COEFF_FN, C.c_void_p]),
+    "ptf_set_velocity_expr": (C.c_int32, [_H, C.c_int32, C.c_char_p]),
     "ptf_set_layered_velocity": (C.c_int32, [_H, _DP, _DP, _DP]),
     "ptf_set_c": (C.c_int32, [_H, _DP, C.c_int32]),
     "ptf_get_c": (C.c_int32, [_H, _DP]),

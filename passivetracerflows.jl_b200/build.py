@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libptf_b200.so")
-SOURCES = ["ptf_api.cu", "engine_cufft.cu", "engine_fused.cu", "engine_fused1d.cu", "engine_mqg.cu", "engine_slab2d.cu"]
+SOURCES = ["ptf_api.cu", "engine_cufft.cu", "engine_fused.cu", "engine_fused1d.cu", "engine_mqg.cu", "engine_slab2d.cu", "expr_flow.cu"]
 FUSED_SIZES = [256, 512, 1024, 2048, 4096]   # fused_inst.cu is compiled once per transform length (in parallel)
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -61,7 +61,7 @@ def build(force=False, verbose=False, with_nccl=True):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}")
-    link = [nvcc, "-shared", *ARCH, "-o", LIB, *objs, "-L/usr/local/cuda/lib64", "-lcufft",
+    link = [nvcc, "-shared", *ARCH, "-o", LIB, *objs, "-L/usr/local/cuda/lib64", "-lcufft", "-lnvrtc",
             "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     if with_nccl:
         link += ["-lnccl"]

@@ -13,6 +13,7 @@
 
 #include "ptf_pointwise.cuh"
 #include "ptf_velocity.cuh"
+#include "expr_flow.h"
 
 #ifdef PTF_WITH_NCCL
 #include <nccl.h>
@@ -554,6 +555,17 @@ class CufftEngine final : public Engine {
     vs.set_external(comp, dev, count);
     sync_vel();
   }
+  void set_velocity_expr(int comp, const char* expr) override {
+    ef.set(comp, expr);
+    bool all = true;
+    for (int a = 0; a < nd; ++a) all = all && !ef.expr[a].empty();
+    if (all && ef.stale) {
+      PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+      ef.compile(nd);
+      drop_graphs();
+    }
+  }
+  void set_flow_time(double t) override { ef.set_time(t, ctx.stream); }
 
   // ---------------- state ----------------
   void set_c(const double* c_host, bool replicate) override {
@@ -646,7 +658,10 @@ class CufftEngine final : public Engine {
     VelArgs va = vs.va;
     for (int c = 0; c < 3; ++c)
       if (va.sep[c].zt) va.sep[c].zt += g.zoff;
-    k_product<3><<<pg, 256, 0, ctx.stream>>>(gr[0].p, gr[1].p, gr[2].p, va, g.nx, g.ny, g.nzl);
+    if (va.kind == PTF_FLOW_EXPR)
+      ef.launch(ctx.stream, (int)pg.x, (int)g.B, gr[0].p, gr[1].p, gr[2].p, g.nx, g.ny, g.nzl, 0, g.zoff, g);
+    else
+      k_product<3><<<pg, 256, 0, ctx.stream>>>(gr[0].p, gr[1].p, gr[2].p, va, g.nx, g.ny, g.nzl);
     ++own_launches;
     // forward: chunked 2-D r2c + pack, exchanges pipelined on the comm stream, then the z transform
     const int nch = n_chunks;
@@ -685,7 +700,7 @@ class CufftEngine final : public Engine {
     pt.begin(4);
     int64_t half = g.lpts() / 2;
     VelArgs va = vs.va;
-    if (va.kind != PTF_FLOW_SEPARABLE)
+    if (va.kind != PTF_FLOW_SEPARABLE && va.kind != PTF_FLOW_EXPR)
       for (int c = 0; c < nd; ++c)
         if (!va.arr[c]) throw Error(PTF_EINVAL, "velocity fields have not been set (ptf_set_velocity / callback)");
     if (g.slab)
@@ -694,7 +709,9 @@ class CufftEngine final : public Engine {
     dim3 pg((unsigned)flat_blocks(half), (unsigned)g.B, 1);
     const double* g1 = nd >= 2 ? gr[1].p : gr[0].p;
     const double* g2 = nd >= 3 ? gr[2].p : gr[0].p;
-    if (nd == 1)
+    if (va.kind == PTF_FLOW_EXPR)
+      ef.launch(ctx.stream, (int)pg.x, (int)g.B, gr[0].p, g1, g2, g.nx, g.ny, g.nzl, 0, g.slab ? g.zoff : 0, g);
+    else if (nd == 1)
       k_product<1><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nzl);
     else if (nd == 2)
       k_product<2><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nzl);
@@ -854,6 +871,7 @@ class CufftEngine final : public Engine {
   DevBuf<double2> sol, s1, s2, acc, n1, dh[3];
   DevBuf<double> gr[3];
   VelocityStore vs;
+  ExprFlow ef;
   DevBuf<double> cE, cE2, cZ, cA, cB, cG;
   DevBuf<char> work;
   PhaseTimer pt;

@@ -28,6 +28,7 @@
 #include "ptf_internal.h"
 #include "ptf_pointwise.cuh"
 #include "ptf_velocity.cuh"
+#include "expr_flow.h"
 
 namespace ptf {
 namespace {
@@ -349,6 +350,15 @@ class Slab2DEngine final : public Engine {
     sync_vel();
   }
   void set_velocity_coeffs(int comp, int nterms, const double* a) override { vs.set_coeffs(comp, nterms, a); }
+  void set_velocity_expr(int comp, const char* expr) override {
+    ef.set(comp, expr);
+    if (!ef.expr[0].empty() && !ef.expr[1].empty() && ef.stale) {
+      PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+      ef.compile(2);
+      drop_graphs();
+    }
+  }
+  void set_flow_time(double t) override { ef.set_time(t, ctx.stream); }
   void set_layered_shift(const double*) override {
     throw Error(PTF_EUNSUPPORTED, "layered flows are not slab-decomposed (shard the layers: PTF_DECOMP_BATCH)");
   }
@@ -402,9 +412,13 @@ class Slab2DEngine final : public Engine {
     cudaEvent_t a1 = inv_begin(1, F[1].p);   // ... while field 1 is y-transformed and packed
     inv_end(0, a0, G[0].p);
     inv_end(1, a1, G[1].p);
-    if (vs.va.kind != PTF_FLOW_SEPARABLE && (!vs.va.arr[0] || !vs.va.arr[1]))
-      throw Error(PTF_EINVAL, "velocity fields have not been set (ptf_set_velocity / callback)");
-    k2_product<<<blocks(nreal / 2), 256, 0, ctx.stream>>>(G[0].p, G[1].p, vs.va, nx, nyp, ny, g.ypoff);
+    if (vs.va.kind == PTF_FLOW_EXPR) {
+      ef.launch(ctx.stream, blocks(nreal / 2), 1, G[0].p, G[1].p, G[1].p, nx, nyp, 1, g.ypoff, 0, g);
+    } else {
+      if (vs.va.kind != PTF_FLOW_SEPARABLE && (!vs.va.arr[0] || !vs.va.arr[1]))
+        throw Error(PTF_EINVAL, "velocity fields have not been set (ptf_set_velocity / callback)");
+      k2_product<<<blocks(nreal / 2), 256, 0, ctx.stream>>>(G[0].p, G[1].p, vs.va, nx, nyp, ny, g.ypoff);
+    }
     ++own_launches;
     fwd(G[0].p, F[0].p);
   }
@@ -530,6 +544,7 @@ class Slab2DEngine final : public Engine {
   DevBuf<double> cE, cE2, cZ, cA, cB, cG;
   DevBuf<char> work;
   VelocityStore vs;
+  ExprFlow ef;
   cufftHandle plan_y = 0, plan_xi = 0, plan_xf = 0, plan_yT = 0, plan_Ty = 0;
   bool strided = false;
   cudaStream_t s_comm = nullptr;

@@ -136,7 +136,7 @@ void build_context(ptf_handle* h, const ptf_desc* d) {
   PTF_REQUIRE(d->nranks >= 1 && d->rank >= 0 && d->rank < d->nranks, "bad rank / nranks");
   int base = d->stepper & ~PTF_STEPPER_FILTERED;
   PTF_REQUIRE(base >= PTF_STEPPER_FORWARD_EULER && base <= PTF_STEPPER_AB3, "unknown stepper");
-  PTF_REQUIRE(d->flow_kind >= PTF_FLOW_STEADY && d->flow_kind <= PTF_FLOW_LAYERED, "unknown flow_kind");
+  PTF_REQUIRE(d->flow_kind >= PTF_FLOW_STEADY && d->flow_kind <= PTF_FLOW_EXPR, "unknown flow_kind");
   c.st.base = base;
   c.st.filtered = (d->stepper & PTF_STEPPER_FILTERED) != 0;
 
@@ -269,6 +269,8 @@ void run_velocity_providers(ptf_handle* h) {
     h->vel_fn(h->vel_user, c.t, h->pinned_vel[0], nd >= 2 ? h->pinned_vel[1] : nullptr,
               nd >= 3 ? h->pinned_vel[2] : nullptr);
     for (int a = 0; a < nd; ++a) h->engine->set_velocity(a, h->pinned_vel[a], count);
+  } else if (c.d.flow_kind == PTF_FLOW_EXPR) {
+    h->engine->set_flow_time(c.t);   // evaluated at clock.t for all stages of the step (TAD.jl:701,718,737)
   } else if (c.d.flow_kind == PTF_FLOW_SEPARABLE && h->coeff_fn) {
     for (int a = 0; a < nd; ++a) {
       int nt = h->sep_nterms[a];
@@ -284,7 +286,7 @@ void do_steps(ptf_handle* h, int64_t nsteps) {
   Context& c = h->ctx;
   // no per-step host input (steady arrays, or a separable flow without a coefficient callback): the engine may run
   // the whole call in one launch
-  const bool per_step_input = c.d.flow_kind == PTF_FLOW_CALLBACK ||
+  const bool per_step_input = c.d.flow_kind == PTF_FLOW_CALLBACK || c.d.flow_kind == PTF_FLOW_EXPR ||
                               (c.d.flow_kind == PTF_FLOW_SEPARABLE && h->coeff_fn != nullptr);
   if (!per_step_input && nsteps > 0 && h->engine->step_many(c.step, nsteps)) {
     for (int64_t i = 0; i < nsteps; ++i) c.t += c.dt;  // same rounding as FF's clock.t += dt per step
@@ -420,6 +422,10 @@ int32_t ptf_create(const ptf_desc* d, ptf_handle** out) {
     std::string why;
     int want = d->engine;
     const bool one_d = h->ctx.g.ndim == 1;
+    const bool expr_flow = d->flow_kind == PTF_FLOW_EXPR;
+    if (expr_flow && want == PTF_ENGINE_FUSED)
+      throw Error(PTF_EUNSUPPORTED, "fused engine: expression flows (PTF_FLOW_EXPR) run on the cuFFT pipelines");
+    if (expr_flow && want == PTF_ENGINE_AUTO) want = PTF_ENGINE_CUFFT;
     if (h->ctx.g.slab2d) {
       if (want == PTF_ENGINE_FUSED) throw Error(PTF_EUNSUPPORTED, "fused engine: 2-D slab decomposition runs on the cuFFT pipeline");
       h->engine = make_slab2d_engine(h->ctx);
@@ -506,6 +512,15 @@ int32_t ptf_set_velocity_separable(ptf_handle* h, int32_t comp, int32_t nterms, 
     PTF_REQUIRE(comp >= 0 && comp < h->ctx.g.ndim, "velocity component out of range");
     h->engine->set_velocity_separable(comp, nterms, xtab, ytab, ztab, coeff0);
     h->sep_nterms[comp] = nterms;
+  });
+}
+
+int32_t ptf_set_velocity_expr(ptf_handle* h, int32_t comp, const char* expr) {
+  if (!h || !expr) return PTF_EINVAL;
+  return guarded(h, [&]() {
+    PTF_REQUIRE(h->ctx.d.flow_kind == PTF_FLOW_EXPR, "problem was not created with PTF_FLOW_EXPR");
+    PTF_REQUIRE(comp >= 0 && comp < h->ctx.g.ndim, "velocity component out of range");
+    h->engine->set_velocity_expr(comp, expr);
   });
 }
 

@@ -138,6 +138,11 @@ class Engine {
     (void)comp; (void)dev; (void)count;
     throw Error(PTF_EUNSUPPORTED, "this engine cannot read device-resident velocity fields");
   }
+  virtual void set_velocity_expr(int comp, const char* expr) {  // PTF_FLOW_EXPR
+    (void)comp; (void)expr;
+    throw Error(PTF_EUNSUPPORTED, "this engine does not support expression flows (PTF_FLOW_EXPR runs on the cuFFT pipelines)");
+  }
+  virtual void set_flow_time(double t) { (void)t; }  // PTF_FLOW_EXPR: clock.t of the step about to run
   virtual void set_c(const double* c_host, bool replicate) = 0;
   virtual void get_c(double* c_host) = 0;
   virtual void set_sol(const double* s_host) = 0;
