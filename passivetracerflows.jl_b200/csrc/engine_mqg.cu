@@ -35,6 +35,8 @@ struct MqgSpecArgs {
   AxisTables ax;       // kx, ky; L = −ν|k|^{2nν} through (kappa_h, n_kappa_h); filter; dealias ranges
   int64_t nkr, ny;
   double mu, scale;
+  int uniform_bg;                    // Qx == 0 and Qy uniform per layer: the background term is applied spectrally
+  double qy[PTF_MQG_MAX_LAYERS];     // that uniform Qy_j
   CombinePtrs P;
   CombineArgs A;
 };
@@ -51,7 +53,13 @@ __global__ void __launch_bounds__(128) k_mqg_spec(MqgSpecArgs a) {
   if (COMBINE) {
 #pragma unroll
     for (int j = 0; j < NL; ++j) {
-      const double2 f0 = a.spec3[(0 * NL + j) * plane + i];
+      double2 f0;
+      if (a.uniform_bg) {   // rfft(v*Qy_j) = Qy_j * i kr psi-hat_j (v = irfft(i kr psi-hat), Qy_j a constant); u*Qx = 0
+        const double2 pj = a.psih[(int64_t)j * plane + i];
+        f0 = make_double2(-a.qy[j] * kx * pj.y, a.qy[j] * kx * pj.x);
+      } else {
+        f0 = a.spec3[(0 * NL + j) * plane + i];
+      }
       const double2 f1 = a.spec3[(1 * NL + j) * plane + i];
       const double2 f2 = a.spec3[(2 * NL + j) * plane + i];
       // N̂ = −P̂0 − i kr P̂1 − i l P̂2
@@ -101,7 +109,7 @@ __global__ void __launch_bounds__(128) k_mqg_spec(MqgSpecArgs a) {
 
 // phys3 = [u, v, q][NL][ny][nx] -> [u·Qx + v·Qy, u·q, v·q] with u += U(y, layer); two points per thread
 __global__ void __launch_bounds__(256) k_mqg_products(double* phys3, const double* Qx, const double* Qy, const double* U,
-                                                      int64_t nx, int64_t ny, int64_t NL) {
+                                                      int64_t nx, int64_t ny, int64_t NL, int uniform_bg) {
   const int64_t T = nx * ny * NL, half = T / 2, hx = nx / 2;
   double2* u2 = reinterpret_cast<double2*>(phys3);
   double2* v2 = reinterpret_cast<double2*>(phys3 + T);
@@ -112,10 +120,12 @@ __global__ void __launch_bounds__(256) k_mqg_products(double* phys3, const doubl
     const int64_t row = e / hx;   // = layer*ny + y
     const double Us = U[row];
     double2 u = u2[e], v = v2[e], q = q2[e];
-    const double2 qx = qx2[e], qy = qy2[e];
     u.x += Us;
     u.y += Us;
-    u2[e] = make_double2(u.x * qx.x + v.x * qy.x, u.y * qx.y + v.y * qy.y);
+    if (!uniform_bg) {
+      const double2 qx = qx2[e], qy = qy2[e];
+      u2[e] = make_double2(u.x * qx.x + v.x * qy.x, u.y * qx.y + v.y * qy.y);
+    }
     v2[e] = make_double2(u.x * q.x, u.y * q.y);
     q2[e] = make_double2(v.x * q.x, v.y * q.y);
   }
@@ -232,8 +242,8 @@ class MqgSolver {
 
   ~MqgSolver() {
     drop_graphs();
-    if (plan_fwd) cufftDestroy(plan_fwd);
-    if (plan_inv) cufftDestroy(plan_inv);
+    for (cufftHandle p : {plan_fwd, plan_inv, plan_fwd2, plan_inv2})
+      if (p) cufftDestroy(p);
     if (own_stream) cudaStreamDestroy(own_stream);
   }
 
@@ -314,12 +324,20 @@ class MqgSolver {
     PTF_CUFFT(cufftSetAutoAllocation(plan_inv, 0));
     PTF_CUFFT(cufftMakePlanMany64(plan_fwd, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_D2Z, 3 * NL, &wf));
     PTF_CUFFT(cufftMakePlanMany64(plan_inv, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2D, 3 * NL, &wi));
-    size_t w = wf > wi ? wf : wi;
+    // two-field batches: forward of (u q, v q) when the background term is spectral; inverse of (u, v) for updatevars!
+    size_t wf2 = 0, wi2 = 0;
+    PTF_CUFFT(cufftCreate(&plan_fwd2));
+    PTF_CUFFT(cufftCreate(&plan_inv2));
+    PTF_CUFFT(cufftSetAutoAllocation(plan_fwd2, 0));
+    PTF_CUFFT(cufftSetAutoAllocation(plan_inv2, 0));
+    PTF_CUFFT(cufftMakePlanMany64(plan_fwd2, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_D2Z, 2 * NL, &wf2));
+    PTF_CUFFT(cufftMakePlanMany64(plan_inv2, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2D, 2 * NL, &wi2));
+    size_t w = std::max(std::max(wf, wi), std::max(wf2, wi2));
     work.alloc(w ? w : 16, &dev_bytes);
-    PTF_CUFFT(cufftSetWorkArea(plan_fwd, work.p));
-    PTF_CUFFT(cufftSetWorkArea(plan_inv, work.p));
-    PTF_CUFFT(cufftSetStream(plan_fwd, stream));
-    PTF_CUFFT(cufftSetStream(plan_inv, stream));
+    for (cufftHandle p : {plan_fwd, plan_inv, plan_fwd2, plan_inv2}) {
+      PTF_CUFFT(cufftSetWorkArea(p, work.p));
+      PTF_CUFFT(cufftSetStream(p, stream));
+    }
   }
 
   // MultiLayerQG.Params: stretching matrix, S⁻¹, background PV gradients Qx, Qy
@@ -411,6 +429,15 @@ class MqgSolver {
           hQy[(size_t)j * pts + y * nx + x] = (qy - stretch_a) - stretch_b;
         }
       }
+    // background term applied spectrally when Qx == 0 and Qy is one constant per layer (no topography, uniform U):
+    // rfft(v*Qy_j) = Qy_j * i kr psi-hat_j exactly, which saves one product field and a third of the forward transforms
+    uniform_bg = std::getenv("PTF_MQG_NO_SPECTRAL_BG") == nullptr;
+    for (int j = 0; j < NL && uniform_bg; ++j) {
+      const double q0 = hQy[(size_t)j * pts];
+      qy_uniform[j] = q0;
+      for (int64_t p = 0; p < pts && uniform_bg; ++p)
+        uniform_bg = hQx[(size_t)j * pts + p] == 0.0 && hQy[(size_t)j * pts + p] == q0;
+    }
     PTF_CUDA(cudaMemcpy(Qx.p, hQx.data(), hQx.size() * sizeof(double), cudaMemcpyHostToDevice));
     PTF_CUDA(cudaMemcpy(Qy.p, hQy.data(), hQy.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
@@ -455,8 +482,7 @@ class MqgSolver {
     PTF_CUDA(cudaStreamSynchronize(stream));
     drop_graphs();
     stream = s;
-    PTF_CUFFT(cufftSetStream(plan_fwd, stream));
-    PTF_CUFFT(cufftSetStream(plan_inv, stream));
+    for (cufftHandle p : {plan_fwd, plan_inv, plan_fwd2, plan_inv2}) PTF_CUFFT(cufftSetStream(p, stream));
   }
 
   // ---- one stage ----
@@ -485,6 +511,8 @@ class MqgSolver {
     a.ny = ny;
     a.mu = d.mu;
     a.scale = 1.0 / (double)pts;
+    a.uniform_bg = uniform_bg ? 1 : 0;
+    for (int j = 0; j < PTF_MQG_MAX_LAYERS; ++j) a.qy[j] = qy_uniform[j];
     a.P = CombinePtrs{sol.p, s1.p, s2.p, acc.p, n1.p, cE.p, cE2.p, cZ.p, cA.p, cB.p, cG.p};
     a.A = CombineArgs{mode, st.filtered ? 1 : 0, dt, la, lb, llast};
     return a;
@@ -494,9 +522,12 @@ class MqgSolver {
     PTF_CUFFT(cufftExecZ2D(plan_inv, Z(spec3.p), phys3.p));
     const int64_t half = pts * NL / 2;
     int blocks = (int)std::min<int64_t>((half + 255) / 256, 148 * 8);
-    k_mqg_products<<<blocks, 256, 0, stream>>>(phys3.p, Qx.p, Qy.p, Ush.p, nx, ny, NL);
+    k_mqg_products<<<blocks, 256, 0, stream>>>(phys3.p, Qx.p, Qy.p, Ush.p, nx, ny, NL, uniform_bg ? 1 : 0);
     ++own_launches;
-    PTF_CUFFT(cufftExecD2Z(plan_fwd, phys3.p, Z(spec3.p)));
+    if (uniform_bg)   // only u*q and v*q need a transform
+      PTF_CUFFT(cufftExecD2Z(plan_fwd2, phys3.p + (int64_t)NL * pts, Z(spec3.p + (int64_t)NL * plane)));
+    else
+      PTF_CUFFT(cufftExecD2Z(plan_fwd, phys3.p, Z(spec3.p)));
     lib_calls += 2;
   }
 
@@ -591,19 +622,22 @@ class MqgSolver {
     t = t_stop;
   }
 
-  // MultiLayerQG.updatevars!: dealias!(sol) in place; ψ̂ = S⁻¹ q̂; u, v, q to physical space (device-resident)
-  void updatevars() {
-    if (!upd_graph || !d.use_graph) {
-      auto body = [&]() {
-        launch_spec<false, true>(spec_args(sol.p, 0));
-        PTF_CUFFT(cufftExecZ2D(plan_inv, Z(spec3.p), vars3.p));
-        ++lib_calls;
-      };
-      if (!d.use_graph) {
-        body();
-        PTF_CUDA(cudaGetLastError());
-        return;
-      }
+  // MultiLayerQG.updatevars!: dealias!(sol) in place; psi-hat = S^-1 q-hat; u, v, q to physical space (device-resident).
+  // full = false transforms u and v only (what the coupled tracer reads): used for all but the last iteration of the
+  // in-library loops, whose intermediate q nobody can observe.
+  void updatevars(bool full = true) {
+    const int gi = full ? 1 : 0;
+    auto body = [&]() {
+      launch_spec<false, true>(spec_args(sol.p, 0));
+      PTF_CUFFT(cufftExecZ2D(full ? plan_inv : plan_inv2, Z(spec3.p), vars3.p));
+      ++lib_calls;
+    };
+    if (!d.use_graph) {
+      body();
+      PTF_CUDA(cudaGetLastError());
+      return;
+    }
+    if (!upd_graph[gi]) {
       int64_t o0 = own_launches, l0 = lib_calls;
       cudaGraph_t graph = nullptr;
       PTF_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
@@ -615,13 +649,13 @@ class MqgSolver {
         throw;
       }
       PTF_CUDA(cudaStreamEndCapture(stream, &graph));
-      cudaError_t e = cudaGraphInstantiate(&upd_graph, graph, 0);
+      cudaError_t e = cudaGraphInstantiate(&upd_graph[gi], graph, 0);
       cudaGraphDestroy(graph);
       PTF_CUDA(e);
       own_launches = o0;
       lib_calls = l0;
     }
-    PTF_CUDA(cudaGraphLaunch(upd_graph, stream));
+    PTF_CUDA(cudaGraphLaunch(upd_graph[gi], stream));
     own_launches += 1;
     lib_calls += 1;
   }
@@ -631,8 +665,10 @@ class MqgSolver {
       if (ge) cudaGraphExecDestroy(ge);
       ge = nullptr;
     }
-    if (upd_graph) cudaGraphExecDestroy(upd_graph);
-    upd_graph = nullptr;
+    for (auto& ge : upd_graph) {
+      if (ge) cudaGraphExecDestroy(ge);
+      ge = nullptr;
+    }
   }
 
   // ---- set / get ----
@@ -718,9 +754,11 @@ class MqgSolver {
   DevBuf<double> phys3, vars3, Qx, Qy, Ush, sinv, dF;
   DevBuf<double> cE, cE2, cZ, cA, cB, cG;
   DevBuf<char> work;
-  cufftHandle plan_fwd = 0, plan_inv = 0;
+  cufftHandle plan_fwd = 0, plan_inv = 0, plan_fwd2 = 0, plan_inv2 = 0;
+  bool uniform_bg = false;
+  double qy_uniform[PTF_MQG_MAX_LAYERS] = {0, 0, 0, 0};
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
-  cudaGraphExec_t upd_graph = nullptr;
+  cudaGraphExec_t upd_graph[2] = {nullptr, nullptr};
   int64_t per_step_own = 0, per_step_lib = 0;
 };
 
@@ -934,7 +972,7 @@ int32_t ptf_mqg_step_timed(ptf_mqg_handle* h, int64_t nsteps, int32_t with_updat
     PTF_CUDA(cudaEventRecord(h->ev0, h->solver->stream));
     for (int64_t i = 0; i < nsteps; ++i) {
       h->solver->steps(1);
-      if (with_updatevars) h->solver->updatevars();
+      if (with_updatevars) h->solver->updatevars(i + 1 == nsteps);
     }
     PTF_CUDA(cudaEventRecord(h->ev1, h->solver->stream));
     PTF_CUDA(cudaEventSynchronize(h->ev1));
@@ -1027,7 +1065,7 @@ int32_t ptf_mqg_step_coupled(ptf_mqg_handle* m, ptf_handle* tracer, int64_t nste
     for (int64_t i = 0; i < nsteps; ++i) {
       ptf::tracer_step_one(tracer);
       s.steps(1);
-      s.updatevars();
+      s.updatevars(i + 1 == nsteps);   // intermediate iterations only need u, v (the tracer's inputs)
     }
     PTF_CUDA(cudaEventRecord(m->ev1, s.stream));
     PTF_CUDA(cudaEventSynchronize(m->ev1));

@@ -230,3 +230,24 @@ def test_error_behaviour_and_lifetimes():
     with pytest.raises(ValueError):
         ad2.stepforward(1)
     ad2.close()
+
+
+def test_spectral_background_term_equals_the_transformed_product(monkeypatch):
+    """With no topography and uniform U the library applies rfft(v·Qy) = Qy·i kr ψ̂ spectrally (one transform less per
+    stage); PTF_MQG_NO_SPECTRAL_BG forces the generic product path — both must agree to rounding."""
+    q0 = None
+    sols = []
+    for force_generic in (False, True):
+        if force_generic:
+            monkeypatch.setenv("PTF_MQG_NO_SPECTRAL_BG", "1")
+        g = P().MultiLayerQG.Problem(2, P().B200(), nx=64, dt=2.5e-3, stepper="FilteredRK4", aliased_fraction=0.0, **EXAMPLE)
+        if q0 is None:
+            q0 = 0.5 * np.random.default_rng(7).standard_normal((2, 64, 64))
+        g.set_q(q0)
+        own0, lib0 = g.launch_count()
+        g.stepforward(10)
+        own1, lib1 = g.launch_count()
+        sols.append((g.sol, lib1 - lib0))
+        g.close()
+    assert rel_l2(sols[0][0], sols[1][0]) < 1e-13
+    assert sols[0][1] == sols[1][1]          # same number of cuFFT calls, smaller batches
