@@ -91,3 +91,34 @@ class FakeMQGWithGrid:
     class _G:
         nx, ny, Lx, Ly = 16, 16, 6.28, 6.28
     grid = _G()
+
+
+def test_mqg_descriptor_layout_matches(capi):
+    """ptf_mqg_desc (MultiLayerQG.Problem keyword arguments): ctypes mirror and C struct agree; GeophysicalFlows defaults."""
+    lib = capi.load()
+    d = capi.PtfMqgDesc()
+    assert lib.ptf_mqg_desc_init(C.byref(d)) == 0
+    assert d.struct_size == C.sizeof(capi.PtfMqgDesc)
+    assert d.nlayers == 2 and d.nx == 128 and d.ny == 128 and abs(d.Lx - 6.283185307179586) < 1e-15
+    assert d.f0 == 1.0 and d.beta == 0.0 and d.mu == 0.0 and d.nu == 0.0 and d.n_nu == 1 and d.dt == 0.01
+    assert d.stepper == capi.STEPPER_IDS["RK4"] and abs(d.aliased_fraction - 1 / 3) < 1e-16 and d.use_graph == 1
+    assert not d.H and not d.b and not d.U and not d.eta
+
+
+def test_mqg_and_expression_entry_points_fail_loudly_without_a_gpu(capi):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    lib = capi.load()
+    d = capi.PtfMqgDesc()
+    lib.ptf_mqg_desc_init(C.byref(d))
+    import numpy as np
+    H = np.array([0.5, 0.5])
+    b = np.array([-1.0, -1.2])
+    d.H, d.b = capi.as_dp(H), capi.as_dp(b)
+    h = C.c_void_p()
+    assert lib.ptf_mqg_create(C.byref(d), C.byref(h)) == capi.ENODEVICE and not h.value
+    assert b"no CPU fallback" in lib.ptf_mqg_last_error(None)
+    import ptf_b200 as P
+    with pytest.raises(capi.PtfError):
+        P.Problem(P.B200(), P.ExpressionFlow("sin(x)", "cos(y)"), nx=64)
