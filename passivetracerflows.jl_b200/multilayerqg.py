@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi
-from .tracer_advection_diffusion import B200, Clock, Grid, _parse_stepper
+from .tracer_advection_diffusion import B200, Clock, Equation, Grid, TimeStepper, _parse_stepper
 
 
 @dataclass
@@ -83,7 +83,8 @@ class MultiLayerQGProblem:
         self.grid = Grid(nx=nx, Lx=Lx, ny=ny, Ly=Ly, ndim=2, device=dev)
         self.params = MQGParams(nlayers=nl, f0=float(f0), beta=float(beta), H=H, b=b, U=U, mu=float(mu), nu=float(nu),
                                 nnu=int(nnu))
-        self.stepper = self.timestepper = stepper
+        self.stepper = stepper
+        self.timestepper = TimeStepper(stepper, self.grid)     # .filter is read at examples/…:64
         self.clock = Clock(dt=float(dt))
         d = _capi.PtfMqgDesc()
         self._lib.ptf_mqg_desc_init(C.byref(d))
@@ -126,6 +127,18 @@ class MultiLayerQGProblem:
             self.close()
         except Exception:
             pass
+
+    @property
+    def eqn(self) -> Equation:
+        """Hyperviscosity ``L = −ν·Krsq^nν`` with ``L[0, 0] = 0``, one copy per layer."""
+        g, p = self.grid, self.params
+        Ksq = g.kr[None, :] ** 2 + g.l[:, None] ** 2
+        hyper = np.ones_like(Ksq)
+        for _ in range(p.nnu):
+            hyper = hyper * Ksq
+        L = -p.nu * hyper
+        L[0, 0] = 0.0
+        return Equation(L=np.ascontiguousarray(np.broadcast_to(L, self._sshape)), dims=self._sshape)
 
     # ---- state ----
     @property

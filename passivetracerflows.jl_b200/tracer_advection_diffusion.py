@@ -170,6 +170,60 @@ def gridpoints(grid: Grid):
     return tuple(out) if grid.ndim > 1 else out[0]
 
 
+def makefilter(grid: "Grid", order: float = 4.0, innerK: float = 2.0 / 3.0, outerK: float = 1.0, tol: float = 1e-15):
+    """FourierFlows ``makefilter(grid)`` (FF utils.jl): 1 for K < innerK, exp(−decay·(K − innerK)^order) beyond, with
+    K = sqrt(Σ (k_a·d_a/π)²).  Host mirror of what the library evaluates in registers; users read it through
+    ``prob.timestepper.filter`` (examples/turbulent_advection-diffusion.jl:64)."""
+    shp = grid.sshape
+    nd = grid.ndim
+    ks = (grid.kr, grid.l, grid.m)[:nd]
+    ds = (grid.dx, grid.dy, grid.dz)[:nd]
+    Ksq = 0.0
+    for a in range(nd):
+        v = [1] * nd
+        v[nd - 1 - a] = len(ks[a])
+        Ksq = Ksq + (ks[a].reshape(v) * ds[a] / np.pi) ** 2
+    K = np.sqrt(Ksq)
+    decay = -math.log(tol) / (outerK - innerK) ** order
+    return np.ascontiguousarray(np.broadcast_to(np.where(K < innerK, 1.0, np.exp(-decay * (K - innerK) ** order)), shp))
+
+
+class TimeStepper:
+    """Mirror of the FourierFlows time-stepper object: behaves like its name (``prob.timestepper == "FilteredRK4"``)
+    and exposes ``filter`` for the Filtered steppers."""
+
+    def __init__(self, name: str, grid: "Grid"):
+        self.name = name
+        self._grid = grid
+        self._filter = None
+
+    @property
+    def filter(self):
+        if not self.name.startswith("Filtered"):
+            raise AttributeError(f"{self.name}TimeStepper has no field filter")
+        if self._filter is None:
+            self._filter = makefilter(self._grid)
+        return self._filter
+
+    def __eq__(self, other):
+        return self.name == (other.name if isinstance(other, TimeStepper) else other)
+
+    def __hash__(self):
+        return hash(self.name)
+
+    def __repr__(self):
+        return f"{self.name}TimeStepper"
+
+    __str__ = lambda self: self.name
+
+
+@dataclass
+class Equation:
+    """``prob.eqn``: the diagonal linear operator as a host array (TAD.jl:502-566; MultiLayerQG hyperviscosity)."""
+    L: np.ndarray
+    dims: tuple
+
+
 @dataclass
 class Vars:
     """``prob.vars``: host mirrors refreshed by ``updatevars`` (TAD.jl:579-636)."""
@@ -215,7 +269,7 @@ class TracerProblem:
         self.grid = grid
         self.params = params
         self.stepper = stepper
-        self.timestepper = stepper
+        self.timestepper = TimeStepper(stepper, grid)
         self.clock = Clock(dt=float(dt))
         self.nbatch = int(nbatch)
         self.dev = dev
@@ -272,6 +326,31 @@ class TracerProblem:
         self._vel_funcs = None
         self._mqg = None
         self._mqg_on_device = False
+
+    @property
+    def eqn(self) -> Equation:
+        """``prob.eqn`` with ``L = −κkr² − ηl² − ιm² − κh·Krsq^nκh`` in the reference's operation order (TAD.jl:502-566)."""
+        g, p, nd = self.grid, self.params, self.grid.ndim
+
+        def ax(a, k):
+            v = [1] * nd
+            v[nd - 1 - a] = len(k)
+            return k.reshape(v)
+        kr2 = ax(0, g.kr) ** 2
+        L, Ksq = -p.kappa * kr2, kr2
+        if nd >= 2:
+            l2 = ax(1, g.l) ** 2
+            L, Ksq = L - p.eta * l2, Ksq + l2
+        if nd >= 3:
+            m2 = ax(2, g.m) ** 2
+            L, Ksq = L - p.iota * m2, Ksq + m2
+        hyper = np.ones_like(Ksq)
+        for _ in range(int(p.n_kappa_h)):
+            hyper = hyper * Ksq
+        L = np.broadcast_to(L - p.kappa_h * hyper, g.sshape)
+        if self.nbatch > 1:
+            L = np.broadcast_to(L, (self.local_nbatch,) + g.sshape)     # copied into each layer (TAD.jl:561-563)
+        return Equation(L=np.ascontiguousarray(L), dims=L.shape)
 
     # ---- lifetime ----
     def close(self):

@@ -122,3 +122,27 @@ def test_mqg_and_expression_entry_points_fail_loudly_without_a_gpu(capi):
     import ptf_b200 as P
     with pytest.raises(capi.PtfError):
         P.Problem(P.B200(), P.ExpressionFlow("sin(x)", "cos(y)"), nx=64)
+
+
+def test_host_mirrors_of_filter_and_linear_operator_match_the_oracle():
+    """prob.timestepper.filter (examples/turbulent_advection-diffusion.jl:64) and prob.eqn.L are host-side mirrors of what
+    the library evaluates in registers; they must equal the oracle's arrays bit for bit."""
+    import numpy as np
+    import ptf_b200 as P
+    from oracle.ptf_oracle import Grid as OGrid, linear_operator, make_filter
+    T = P.tracer_advection_diffusion
+    for n, L in (((48,), (3.0,)), ((32, 48), (2 * np.pi, 4.0)), ((16, 24, 32), (2 * np.pi, 4.0, 3.0))):
+        nd = len(n)
+        kw = dict(zip(("nx", "ny", "nz"), n))
+        kw.update(dict(zip(("Lx", "Ly", "Lz"), L)))
+        g = T.Grid(ndim=nd, **kw)
+        og = OGrid(n, L)
+        assert np.array_equal(T.makefilter(g), make_filter(og))
+        ts = T.TimeStepper("FilteredRK4", g)
+        assert ts == "FilteredRK4" and str(ts) == "FilteredRK4" and np.array_equal(ts.filter, make_filter(og))
+        with pytest.raises(AttributeError):
+            T.TimeStepper("RK4", g).filter
+        stub = T.TracerProblem.__new__(T.TracerProblem)      # eqn needs no device
+        stub.grid, stub.nbatch, stub.local_nbatch = g, 1, 1
+        stub.params = T.Params(kappa=0.01, eta=0.02, iota=0.005, kappa_h=1e-6, n_kappa_h=2)
+        assert np.array_equal(stub.eqn.L, linear_operator(og, (0.01, 0.02, 0.005)[:nd], 1e-6, 2))
