@@ -561,8 +561,8 @@ class CufftEngine final : public Engine {
     for (int a = 0; a < nd; ++a) all = all && !ef.expr[a].empty();
     if (all && ef.stale) {
       PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+      drop_graphs();   // before the old module (referenced by captured kernel nodes) is unloaded
       ef.compile(nd);
-      drop_graphs();
     }
   }
   void set_flow_time(double t) override { ef.set_time(t, ctx.stream); }

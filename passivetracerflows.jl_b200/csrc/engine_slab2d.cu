@@ -354,8 +354,8 @@ class Slab2DEngine final : public Engine {
     ef.set(comp, expr);
     if (!ef.expr[0].empty() && !ef.expr[1].empty() && ef.stale) {
       PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+      drop_graphs();   // before the old module (referenced by captured kernel nodes) is unloaded
       ef.compile(2);
-      drop_graphs();
     }
   }
   void set_flow_time(double t) override { ef.set_time(t, ctx.stream); }

@@ -454,6 +454,10 @@ class TracerProblem:
             self._keep.append(fn)
             _capi.check(self._lib.ptf_set_coeff_callback(self._h, fn, None), self._h)
 
+    def set_velocity_expr(self, comp: int, expr: str):
+        """Replace one component of an ``ExpressionFlow`` (recompiles the product kernel once all components are set)."""
+        _capi.check(self._lib.ptf_set_velocity_expr(self._h, int(comp), str(expr).encode()), self._h)
+
     def set_layered_velocity(self, u, v, U=None):
         """MQG coupling: u = MQGprob.vars.u (+U broadcast over x), v = MQGprob.vars.v (TAD.jl:795-796)."""
         u = np.ascontiguousarray(u, dtype=np.float64)

@@ -80,3 +80,24 @@ def test_expr_flow_errors():
         P().Problem(P().B200(), P().ExpressionFlow("sin(x); while(1){}", "0.0"), nx=64)
     with pytest.raises(P()._capi.PtfError):
         P().Problem(P().B200(engine="fused"), P().ExpressionFlow("sin(x)", "cos(y)"), nx=256)
+
+
+def test_expr_flow_can_be_replaced_between_steps():
+    n, L = (64, 64), (2 * np.pi, 2 * np.pi)
+    prob = P().Problem(P().B200(), P().ExpressionFlow("cos(x)*sin(y)", "-sin(x)*cos(y)"), nx=64, kappa=0.01, dt=5e-3,
+                       stepper="RK4")
+    X, Y = P().gridpoints(prob.grid)
+    c0 = np.exp(-((X - 0.2) ** 2 + (Y - 0.2) ** 2) / 0.3)
+    f1 = [lambda x, y, t: np.cos(x) * np.sin(y), lambda x, y, t: -np.sin(x) * np.cos(y)]
+    f2 = [lambda x, y, t: 0.5 + 0.1 * t + 0 * x, lambda x, y, t: -np.sin(x) * np.cos(y)]
+    o = OracleProblem(n=n, L=L, kappa=(0.01, 0.01), dt=5e-3, stepper="RK4", velocity=f1, steady=False)
+    o.set_c(c0)
+    prob.set_c(c0)
+    o.stepforward(3)
+    prob.stepforward(3)
+    o.vel_funcs = f2
+    prob.set_velocity_expr(0, "0.5 + 0.1*t")          # recompiles; the captured step graph is rebuilt
+    o.stepforward(3)
+    prob.stepforward(3)
+    assert rel_l2(o.updatevars(), prob.updatevars()) < 6 * TOL_STEP
+    prob.close()
