@@ -110,3 +110,21 @@ def test_slab2d_parity_two_ranks():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SLAB2D PARITY OK" in r.stdout
+
+
+def test_slab2d_chunked_forward_pipeline_single_rank(monkeypatch):
+    """PTF_SLAB2D_CHUNKS pipelines the forward transform in row chunks (default 4 when P > 1); with P = 1 the same code
+    path runs with local copies instead of the exchange."""
+    monkeypatch.setenv("PTF_SLAB2D_CHUNKS", "4")
+    nx, ny, L = 96, 64, (2 * np.pi, 4.0)
+    prob = P().Problem(P().B200(decomposition="slab"), P().TwoDAdvectingFlow(u=U, v=V), nx=nx, Lx=L[0], ny=ny, Ly=L[1],
+                       stepper="RK4", kappa=0.01, eta=0.02, dt=2e-3)
+    X, Y = P().gridpoints(prob.grid)
+    o = OracleProblem(n=(nx, ny), L=L, kappa=(0.01, 0.02), dt=2e-3, stepper="RK4", velocity=[U(X, Y), V(X, Y)], steady=True)
+    o.set_c(_c0(X, Y))
+    prob.set_c(_c0(X, Y))
+    assert rel_l2(o.sol, prob.sol) < 1e-14
+    o.stepforward(5)
+    prob.stepforward(5)
+    assert rel_l2(o.updatevars(), prob.updatevars()) < 5 * TOL_STEP
+    prob.close()
