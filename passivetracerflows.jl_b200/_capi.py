@@ -152,6 +152,29 @@ class PtfError(RuntimeError):
         self.status = status
 
 
+def _preload_nccl():
+    """libptf_b200.so needs ``libnccl.so.2``.  PyTorch bundles a NEWER NCCL under the same SONAME than the system one; the
+    dynamic loader keeps whichever copy is loaded first, so loading this library before ``import torch`` would pin the
+    older system copy and break torch (undefined symbol ncclDevCommCreate).  Loading the bundled copy first (when there
+    is one) makes the order irrelevant; the few stable entry points used here (send/recv/group/all-reduce/broadcast)
+    exist in both."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    if spec is None or not spec.submodule_search_locations:
+        return
+    for base in spec.submodule_search_locations:
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL if hasattr(C, "RTLD_GLOBAL") else 0)
+            except OSError:
+                pass
+            return
+
+
 def load():
     """Load libptf_b200.so.  Fails loudly when the CUDA extension has not been built: there is no fallback."""
     global _lib
@@ -160,6 +183,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is missing: build it with `python passivetracerflows.jl_b200/build.py` "
                           "(__graft_entry__.build()).  This package has no CPU / PyTorch fallback.")
+    _preload_nccl()
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL if hasattr(C, "RTLD_GLOBAL") else 0)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)

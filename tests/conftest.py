@@ -14,11 +14,9 @@ def pytest_configure(config):
 
 
 def has_gpu():
-    try:
-        import torch
-        return torch.cuda.is_available()
-    except Exception:
-        return False
+    # A broken torch import must fail the run loudly, never turn every GPU test into a silent skip.
+    import torch
+    return torch.cuda.is_available()
 
 
 def pytest_collection_modifyitems(config, items):
