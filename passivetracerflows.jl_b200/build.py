@@ -7,8 +7,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libptf_b200.so")
-SOURCES = ["ptf_api.cu", "engine_cufft.cu", "engine_fused.cu", "engine_fused1d.cu", "engine_mqg.cu", "engine_slab2d.cu", "expr_flow.cu"]
-FUSED_SIZES = [256, 512, 1024, 2048, 4096]   # fused_inst.cu is compiled once per transform length (in parallel)
+SOURCES = ["ptf_api.cu", "engine_cufft.cu", "engine_fused.cu", "engine_fused3d.cu", "engine_fused1d.cu", "engine_mqg.cu",
+           "engine_slab2d.cu", "expr_flow.cu"]
+FUSED_SIZES = [64, 128, 256, 512, 1024, 2048, 4096]   # fused_inst.cu is compiled once per transform length (in parallel)
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

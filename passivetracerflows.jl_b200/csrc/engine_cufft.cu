@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(256) k_replicate(double* __restrict__ c, int64
 template <int ND>
 __global__ void __launch_bounds__(256) k_product(double* __restrict__ g0, const double* __restrict__ g1,
                                                  const double* __restrict__ g2, VelArgs va, int64_t nx, int64_t ny,
-                                                 int64_t nz) {
+                                                 int64_t nz, int64_t nzg, int64_t zoff) {
+  // nz = local planes; separable z tables are global, [nterms][nzg], and this rank's first plane is zoff
   int64_t npts = nx * ny * nz;
   int64_t half = npts >> 1;
   int64_t b = blockIdx.y;
@@ -134,14 +135,14 @@ __global__ void __launch_bounds__(256) k_product(double* __restrict__ g0, const 
       int64_t p = e * 2;
       int64_t i = p % nx;
       int64_t j = (p / nx) % ny;
-      int64_t k = p / (nx * ny);
-      u = make_double2(sep_eval(va.sep[0], i, j, k, nx, ny, nz, ND), sep_eval(va.sep[0], i + 1, j, k, nx, ny, nz, ND));
+      int64_t k = p / (nx * ny) + zoff;
+      u = make_double2(sep_eval(va.sep[0], i, j, k, nx, ny, nzg, ND), sep_eval(va.sep[0], i + 1, j, k, nx, ny, nzg, ND));
       if (ND >= 2)
-        v = make_double2(sep_eval(va.sep[1], i, j, k, nx, ny, nz, ND),
-                         sep_eval(va.sep[1], i + 1, j, k, nx, ny, nz, ND));
+        v = make_double2(sep_eval(va.sep[1], i, j, k, nx, ny, nzg, ND),
+                         sep_eval(va.sep[1], i + 1, j, k, nx, ny, nzg, ND));
       if (ND >= 3)
-        w = make_double2(sep_eval(va.sep[2], i, j, k, nx, ny, nz, ND),
-                         sep_eval(va.sep[2], i + 1, j, k, nx, ny, nz, ND));
+        w = make_double2(sep_eval(va.sep[2], i, j, k, nx, ny, nzg, ND),
+                         sep_eval(va.sep[2], i + 1, j, k, nx, ny, nzg, ND));
     } else {
       u = reinterpret_cast<const double2*>(va.arr[0] + voff)[e];
       if (ND >= 2) v = reinterpret_cast<const double2*>(va.arr[1] + voff)[e];
@@ -656,12 +657,10 @@ class CufftEngine final : public Engine {
     int64_t half = g.lpts() / 2;
     dim3 pg((unsigned)flat_blocks(half), (unsigned)g.B, 1);
     VelArgs va = vs.va;
-    for (int c = 0; c < 3; ++c)
-      if (va.sep[c].zt) va.sep[c].zt += g.zoff;
     if (va.kind == PTF_FLOW_EXPR)
       ef.launch(ctx.stream, (int)pg.x, (int)g.B, gr[0].p, gr[1].p, gr[2].p, g.nx, g.ny, g.nzl, 0, g.zoff, g);
     else
-      k_product<3><<<pg, 256, 0, ctx.stream>>>(gr[0].p, gr[1].p, gr[2].p, va, g.nx, g.ny, g.nzl);
+      k_product<3><<<pg, 256, 0, ctx.stream>>>(gr[0].p, gr[1].p, gr[2].p, va, g.nx, g.ny, g.nzl, g.nz, g.zoff);
     ++own_launches;
     // forward: chunked 2-D r2c + pack, exchanges pipelined on the comm stream, then the z transform
     const int nch = n_chunks;
@@ -703,20 +702,18 @@ class CufftEngine final : public Engine {
     if (va.kind != PTF_FLOW_SEPARABLE && va.kind != PTF_FLOW_EXPR)
       for (int c = 0; c < nd; ++c)
         if (!va.arr[c]) throw Error(PTF_EINVAL, "velocity fields have not been set (ptf_set_velocity / callback)");
-    if (g.slab)
-      for (int c = 0; c < 3; ++c)
-        if (va.sep[c].zt) va.sep[c].zt += g.zoff;  // separable z tables are global: start at this rank's first plane
+    const int64_t zoff = g.slab ? g.zoff : 0;   // separable z tables are global: [nterms][nz], plane zoff + local k
     dim3 pg((unsigned)flat_blocks(half), (unsigned)g.B, 1);
     const double* g1 = nd >= 2 ? gr[1].p : gr[0].p;
     const double* g2 = nd >= 3 ? gr[2].p : gr[0].p;
     if (va.kind == PTF_FLOW_EXPR)
       ef.launch(ctx.stream, (int)pg.x, (int)g.B, gr[0].p, g1, g2, g.nx, g.ny, g.nzl, 0, g.slab ? g.zoff : 0, g);
     else if (nd == 1)
-      k_product<1><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nzl);
+      k_product<1><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nzl, g.nz, zoff);
     else if (nd == 2)
-      k_product<2><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nzl);
+      k_product<2><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nzl, g.nz, zoff);
     else
-      k_product<3><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nzl);
+      k_product<3><<<pg, 256, 0, ctx.stream>>>(gr[0].p, g1, g2, va, g.nx, g.ny, g.nzl, g.nz, zoff);
     ++own_launches;
     pt.end();
     fwd(gr[0].p, dh[0].p);

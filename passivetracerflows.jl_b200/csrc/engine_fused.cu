@@ -10,6 +10,8 @@ namespace ptf {
   void fused_launch_y_##N(bool has_in, int fam, const void* yargs, int nb, cudaStream_t st, int n_sm);     \
   void fused_launch_x_##N(int vmode, const void* xargs, int nb, cudaStream_t st, int n_sm);                \
   void fused_selftest_##N(int dir, int count, const double2* in, double2* out, const void* tw);
+PTF_DECL_INST(64)
+PTF_DECL_INST(128)
 PTF_DECL_INST(256)
 PTF_DECL_INST(512)
 PTF_DECL_INST(1024)
@@ -18,6 +20,8 @@ PTF_DECL_INST(4096)
 
 #define PTF_DISPATCH_N(n, FN, ...)                                                               \
   switch (n) {                                                                                   \
+    case 64: FN##_64(__VA_ARGS__); break;                                                        \
+    case 128: FN##_128(__VA_ARGS__); break;                                                      \
     case 256: FN##_256(__VA_ARGS__); break;                                                      \
     case 512: FN##_512(__VA_ARGS__); break;                                                      \
     case 1024: FN##_1024(__VA_ARGS__); break;                                                    \
@@ -418,7 +422,7 @@ bool fused_engine_supports(const Context& ctx, std::string* why) {
     return false;
   };
   if (ctx.g.ndim != 2) return no("only 2-D problems (1-D / 3-D run on the cuFFT engine)");
-  if (!is_fused_size(ctx.g.nx) || !is_fused_size(ctx.g.ny)) return no("nx and ny must be powers of two in [256, 4096]");
+  if (!is_fused_size(ctx.g.nx) || !is_fused_size(ctx.g.ny)) return no("nx and ny must be powers of two in [64, 4096]");
   if (ctx.g.B > 65535) return no("batch too large for one launch");
   return true;
 }
@@ -432,7 +436,7 @@ std::unique_ptr<Engine> make_fused_engine(Context& ctx) {
 // Test hook: run `count` independent length-n complex transforms through the hand-written FFT core
 // (dir = -1 / +1), or the TMEM pairing test (dir = 2: transforms along axis 0 of a row-major [n][count] matrix).
 void selftest_fft(int n, int dir, int count, const double* in_host, double* out_host) {
-  PTF_REQUIRE(is_fused_size(n), "selftest_fft: n must be a power of two in [256, 4096]");
+  PTF_REQUIRE(is_fused_size(n), "selftest_fft: n must be a power of two in [64, 4096]");
   PTF_REQUIRE(dir == 1 || dir == -1 || dir == 2, "selftest_fft: dir must be +1, -1 or 2 (pair test)");
   PTF_REQUIRE(count > 0, "selftest_fft: count must be positive");
   PTF_REQUIRE(dir != 2 || count % 2 == 0, "pair test needs an even count");

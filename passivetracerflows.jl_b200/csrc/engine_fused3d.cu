@@ -1,0 +1,544 @@
+// Fused 3-D engine, host side (kernels: fused_kernels.cuh with D3 = true, fused3d_kernels.cuh).  calcN! in 3-D
+// (TAD.jl:771-786 steady, :725-742 time-varying) + the FourierFlows stage combine as four hand-written kernels per
+// stage, no cuFFT on the step path; one process per GPU with z-slabs (physical) / ky-slabs (spectral) when the
+// problem is slab-decomposed, the all-to-all between the y- and z-column kernels moving contiguous blocks that the
+// producing kernels already wrote in the receiver's layout (no pack / unpack passes).
+#include <cmath>
+
+#include "fused3d_kernels.cuh"
+
+#ifdef PTF_WITH_NCCL
+#include <nccl.h>
+#endif
+
+namespace ptf {
+
+#define PTF_DECL_INST3(N)                                                                           \
+  void fused3_prep_##N();                                                                           \
+  void fused3_launch_z_##N(bool has_in, int fam, const void* yargs, cudaStream_t st, int n_sm);     \
+  void fused3_launch_x_##N(int vmode, const void* xargs, int nplanes, cudaStream_t st, int n_sm);   \
+  void fused3_launch_y_##N(bool inverse, const void* y3args, cudaStream_t st, int n_sm);
+PTF_DECL_INST3(64)
+PTF_DECL_INST3(128)
+PTF_DECL_INST3(256)
+PTF_DECL_INST3(512)
+PTF_DECL_INST3(1024)
+
+#define PTF_DISPATCH_N3(n, FN, ...)                                                              \
+  switch (n) {                                                                                   \
+    case 64: FN##_64(__VA_ARGS__); break;                                                        \
+    case 128: FN##_128(__VA_ARGS__); break;                                                      \
+    case 256: FN##_256(__VA_ARGS__); break;                                                      \
+    case 512: FN##_512(__VA_ARGS__); break;                                                      \
+    case 1024: FN##_1024(__VA_ARGS__); break;                                                    \
+    default: throw Error(PTF_EUNSUPPORTED, "fused 3-D engine: unsupported transform length");    \
+  }
+
+namespace {
+
+bool is_fused3_size(int64_t n) { return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024; }
+int ilog2(int64_t v) {
+  int s = 0;
+  while ((int64_t(1) << s) < v) ++s;
+  return s;
+}
+
+class Fused3DEngine final : public Engine {
+ public:
+  explicit Fused3DEngine(Context& c) : ctx(c), g(c.g) {
+    nx = (int)g.nx;
+    ny = (int)g.ny;
+    nz = (int)g.nz;
+    nkx = (int)g.nkr;
+    P = g.slab ? g.P : 1;
+    rank = g.slab ? g.rank : 0;
+    nyl = (int)g.nyl;
+    nzl = (int)g.nzl;
+    nspec = (size_t)nkx * nyl * nz;
+    blk = (size_t)nkx * nyl * nzl;
+    int base = ctx.st.base;
+    auto zalloc = [&](DevBuf<double2>& b) {
+      b.alloc(nspec, &dev_bytes);
+      PTF_CUDA(cudaMemsetAsync(b.p, 0, b.bytes(), ctx.stream));
+    };
+    zalloc(s0);
+    if (base == PTF_STEPPER_RK4 || base == PTF_STEPPER_ETDRK4) zalloc(s1);
+    if (base == PTF_STEPPER_ETDRK4) zalloc(s2);
+    if (base != PTF_STEPPER_FORWARD_EULER) zalloc(acc);
+    if (base == PTF_STEPPER_ETDRK4 || base == PTF_STEPPER_AB3) zalloc(n1);
+    for (auto* b : {&U1, &U2, &U3, &U4, &YA, &YB, &YC}) zalloc(*b);
+    if (P == 1) {
+      ZA = U1.p; ZC = U2.p; RA = U1.p; RC = U2.p; PX = U3.p; PXY = U4.p; RP = U4.p;
+    } else {
+      ZA = U1.p; ZC = U2.p; RA = U3.p; RC = U4.p; PX = U3.p; PXY = U1.p; RP = U4.p;
+    }
+    if (base == PTF_STEPPER_ETDRK4)
+      for (auto* b : {&cE, &cE2, &cZ, &cA, &cB, &cG}) b->alloc(nspec, &dev_bytes);
+    twx.build(nx, &dev_bytes);
+    if (ny != nx) twy_own.build(ny, &dev_bytes);
+    if (nz != nx && nz != ny) twz_own.build(nz, &dev_bytes);
+    vs.init(&g, ctx.stream, ctx.d.flow_kind, &dev_bytes);
+    PTF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx.device));
+    PTF_DISPATCH_N3(nx, fused3_prep);
+    if (ny != nx) PTF_DISPATCH_N3(ny, fused3_prep);
+    if (nz != nx && nz != ny) PTF_DISPATCH_N3(nz, fused3_prep);
+    // cuFFT only at the set_c!/updatevars! boundary: batched 1-D transforms along x of the local planes
+    long long n1d[1] = {nx};
+    size_t wf = 0, wi = 0;
+    PTF_CUFFT(cufftCreate(&plan_fwd));
+    PTF_CUFFT(cufftCreate(&plan_inv));
+    PTF_CUFFT(cufftMakePlanMany64(plan_fwd, 1, n1d, nullptr, 1, 0, nullptr, 1, 0, CUFFT_D2Z, (long long)ny * nzl, &wf));
+    PTF_CUFFT(cufftMakePlanMany64(plan_inv, 1, n1d, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2D, (long long)ny * nzl, &wi));
+    PTF_CUFFT(cufftSetStream(plan_fwd, ctx.stream));
+    PTF_CUFFT(cufftSetStream(plan_inv, ctx.stream));
+    dev_bytes += (int64_t)(wf + wi);
+    on_dt_changed();
+  }
+
+  ~Fused3DEngine() override {
+    drop_graphs();
+    if (plan_fwd) cufftDestroy(plan_fwd);
+    if (plan_inv) cufftDestroy(plan_inv);
+  }
+
+  const char* name() const override { return "fused3d"; }
+  int id() const override { return PTF_ENGINE_FUSED; }
+  cudaStream_t stream() const override { return ctx.stream; }
+
+  Twiddles tw_x() const { return twx.dev(); }
+  Twiddles tw_y() const { return ny != nx ? twy_own.dev() : twx.dev(); }
+  Twiddles tw_z() const { return nz == nx ? twx.dev() : (nz == ny ? tw_y() : twz_own.dev()); }
+
+  // ---------------- velocities ----------------
+  void sync_vel() {
+    if (vs.dirty) drop_graphs();
+    vs.dirty = false;
+  }
+  void set_velocity(int comp, const double* host, int64_t count) override { vs.set_array(comp, host, count); sync_vel(); }
+  void set_velocity_separable(int comp, int nterms, const double* xt, const double* yt, const double* zt,
+                              const double* coeff0) override {
+    vs.set_separable(comp, nterms, xt, yt, zt, coeff0);
+    sync_vel();
+    sep_dirty = true;
+  }
+  void set_velocity_coeffs(int comp, int nterms, const double* a) override {
+    vs.set_coeffs(comp, nterms, a);
+    sep_dirty = true;
+  }
+  // separable flows: the three fields of the step about to run, evaluated at clock.t once (k_sep_fill)
+  void refresh_separable() {
+    if (vs.va.kind != PTF_FLOW_SEPARABLE || !sep_dirty) return;
+    const size_t nreal = (size_t)nx * ny * nzl;
+    for (auto& b : sepv)
+      if (b.n != nreal) b.alloc(nreal, &dev_bytes);
+    k_sep_fill<<<148 * 16, 256, 0, ctx.stream>>>(vs.va, sepv[0].p, sepv[1].p, sepv[2].p, nx, ny, nzl, nz, (int)g.zoff);
+    ++own_launches;
+    sep_dirty = false;
+  }
+  void set_layered_shift(const double*) override {
+    throw Error(PTF_EUNSUPPORTED, "layered flows are 2-D per layer");
+  }
+
+  // ---------------- the exchange between the y- and z-column kernels (the only collective) ----------------
+  void exchange(const double2* send, double2* recv) {
+    if (P == 1) return;  // send and recv are the same buffer
+#ifdef PTF_WITH_NCCL
+    ncclComm_t comm = (ncclComm_t)ctx.nccl_comm;
+    auto ck = [](ncclResult_t r, const char* what) {
+      if (r != ncclSuccess) throw Error(PTF_ENCCL, std::string(what) + ": " + ncclGetErrorString(r));
+    };
+    PTF_CUDA(cudaMemcpyAsync(recv + (size_t)rank * blk, send + (size_t)rank * blk, blk * sizeof(double2),
+                             cudaMemcpyDeviceToDevice, ctx.stream));
+    ck(ncclGroupStart(), "ncclGroupStart");
+    for (int r = 0; r < P; ++r) {
+      if (r == rank) continue;
+      ck(ncclSend(send + (size_t)r * blk, 2 * blk, ncclDouble, r, comm, ctx.stream), "ncclSend");
+      ck(ncclRecv(recv + (size_t)r * blk, 2 * blk, ncclDouble, r, comm, ctx.stream), "ncclRecv");
+    }
+    ck(ncclGroupEnd(), "ncclGroupEnd");
+    ++lib_calls;
+#else
+    (void)send; (void)recv;
+    throw Error(PTF_EUNSUPPORTED, "built without NCCL");
+#endif
+  }
+
+  // ---------------- kernels ----------------
+  YArgs zargs(int mode, double la, double lb, int llast) const {
+    YArgs a;
+    a.Px = RP;
+    a.A = ZA;
+    a.Bf = ZC;
+    a.P = CombinePtrs{s0.p, s1.p, s2.p, acc.p, n1.p, cE.p, cE2.p, cZ.p, cA.p, cB.p, cG.p};
+    a.C = CombineArgs{mode, ctx.st.filtered ? 1 : 0, ctx.dt, la, lb, llast};
+    a.ax = ctx.ax;
+    a.tw = tw_z();
+    a.nkr = nkx * nyl;
+    a.inv_n = 1.0 / (double)g.npts();
+    int slot = mode < 0 ? 0 : next_state_slot(mode);
+    a.next_state = slot == 0 ? s0.p : (slot == 1 ? s1.p : s2.p);
+    for (int q = 0; q < 4; ++q) {
+      a.pf_c[q] = nullptr;
+      a.pf_r[q] = nullptr;
+    }
+    a.pf_ahead = 0;
+    a.ablate = 0;
+    a.stagger = 0;
+    a.first_wave = 0;
+    a.nkx = nkx;
+    a.nyl = nyl;
+    a.yoff = (int)g.yoff;
+    a.nzl = nzl;
+    a.zsh = ilog2(nzl);
+    return a;
+  }
+
+  void run_z(bool has_in, int mode, double la = 0, double lb = 0, int llast = 0, int fam_override = -1,
+             bool unmasked = false) {
+    YArgs a = zargs(mode, la, lb, llast);
+    if (unmasked) a.ax.dealias = 0;   // updatevars! transforms sol as it is stored (TAD.jl:815-821)
+    int fam = (ctx.st.base == PTF_STEPPER_RK4) ? FAM_RK4 : (ctx.st.base == PTF_STEPPER_ETDRK4 ? FAM_ETD : FAM_OTHER);
+    if (fam_override >= 0) fam = fam_override;
+    PTF_DISPATCH_N3(nz, fused3_launch_z, has_in, fam, &a, ctx.stream, n_sm);
+    ++own_launches;
+  }
+
+  Y3Args y3args() const {
+    Y3Args a;
+    a.RA = RA;
+    a.RC = RC;
+    a.YA = YA.p;
+    a.YB = YB.p;
+    a.YC = YC.p;
+    a.PX = PX;
+    a.PXY = PXY;
+    a.ky = ctx.ax.ky;
+    a.tw = tw_y();
+    a.nkx = nkx;
+    a.nyl = nyl;
+    a.nzl = nzl;
+    // l = t + T*e, T = ny/16: rank index = e >> esh with 2^esh = 16/P elements per thread and rank
+    const long long T = ny / 16;
+    a.esh = ilog2(16 / P);
+    a.in_se = T * nzl;                                   // [r][kr][ll][zl]
+    a.in_sr = (long long)blk - (long long)nyl * nzl;
+    a.out_se = T * 8;                                    // [p][kr][zl/8][ll][zl%8]
+    a.out_sr = (long long)blk - (long long)nyl * 8;
+    return a;
+  }
+  void run_yinv() {
+    Y3Args a = y3args();
+    PTF_DISPATCH_N3(ny, fused3_launch_y, true, &a, ctx.stream, n_sm);
+    ++own_launches;
+  }
+  void run_yfwd() {
+    Y3Args a = y3args();
+    PTF_DISPATCH_N3(ny, fused3_launch_y, false, &a, ctx.stream, n_sm);
+    ++own_launches;
+  }
+
+  void run_x() {
+    XArgs a;
+    a.A = YA.p;
+    a.Bf = YB.p;
+    a.Cf = YC.p;
+    a.Px = PX;
+    a.va = vs.va;
+    a.ax = ctx.ax;
+    a.tw = tw_x();
+    a.nkr = nkx;
+    a.ny = ny;
+    a.pf_vel = 0;
+    a.pf_ahead = 0;
+    a.ablate = 0;
+    a.stagger = 0;
+    a.first_wave = 0;
+    a.nzg = nz;
+    a.zoff = (int)g.zoff;
+    int vmode = 0;
+    if (vs.va.kind == PTF_FLOW_SEPARABLE) {
+      if (!sepv[0].p) throw Error(PTF_EINVAL, "separable velocity tables have not been set");
+      for (int c = 0; c < 3; ++c) a.va.arr[c] = sepv[c].p;
+    } else if (!vs.va.arr[0] || !vs.va.arr[1] || !vs.va.arr[2]) {
+      throw Error(PTF_EINVAL, "velocity fields have not been set (ptf_set_velocity / callback)");
+    }
+    PTF_DISPATCH_N3(nx, fused3_launch_x, vmode, &a, nzl, ctx.stream, n_sm);
+    ++own_launches;
+  }
+
+  // A, C of the current sol (fresh state): one z-column launch without input + the exchange
+  void prologue() {
+    run_z(false, -1);
+    exchange(ZA, RA);
+    exchange(ZC, RC);
+    ac_valid = true;
+  }
+
+  void stage(int mode, double la = 0, double lb = 0, int llast = 0) {
+    run_yinv();
+    run_x();
+    run_yfwd();
+    exchange(PXY, RP);
+    run_z(true, mode, la, lb, llast);
+    exchange(ZA, RA);
+    exchange(ZC, RC);
+  }
+
+  // ---------------- boundary ----------------
+  int flat_blocks(int64_t n) const {
+    int64_t b = (n + 255) / 256;
+    int64_t cap = 148 * 16;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+  }
+
+  void set_c(const double* c_host, bool replicate) override {
+    (void)replicate;  // nbatch == 1
+    double* real = reinterpret_cast<double*>(YB.p);
+    const int64_t nreal = (int64_t)nx * ny * nzl;
+    PTF_CUDA(cudaMemcpyAsync(real, c_host, nreal * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    PTF_CUFFT(cufftExecD2Z(plan_fwd, real, reinterpret_cast<cufftDoubleComplex*>(YC.p)));   // [zl][y][kr]
+    ++lib_calls;
+    k_block_px<<<flat_blocks((int64_t)nkx * ny * nzl), 256, 0, ctx.stream>>>(YC.p, PX, nkx, ny, nzl);
+    ++own_launches;
+    run_yfwd();
+    exchange(PXY, RP);
+    run_z(true, CM_STORE, 0, 0, 0, FAM_OTHER);   // sol = FFT_z(...) ; leaves A, C of the new sol behind
+    exchange(ZA, RA);
+    exchange(ZC, RC);
+    ac_valid = true;
+    PTF_CUDA(cudaGetLastError());
+    PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+
+  void get_c(double* c_host) override {
+    if (ctx.ax.dealias) {  // A of the UNMASKED sol (the scratch then no longer holds what the next calcN needs)
+      run_z(false, -1, 0, 0, 0, -1, true);
+      exchange(ZA, RA);
+      ac_valid = false;
+    } else {
+      prologue();          // A = IFFT_z(sol / N) in the plane owners' layout
+    }
+    run_yinv();            // A' = IFFT_y(A)
+    dim3 grid((ny + 31) / 32, (nkx + 31) / 32, nzl), block(32, 8, 1);
+    k_unblock_c2r<<<grid, block, 0, ctx.stream>>>(YA.p, YC.p, nkx, ny, nzl);
+    ++own_launches;
+    double* real = reinterpret_cast<double*>(YB.p);
+    PTF_CUFFT(cufftExecZ2D(plan_inv, reinterpret_cast<cufftDoubleComplex*>(YC.p), real));
+    ++lib_calls;
+    PTF_CUDA(cudaMemcpyAsync(c_host, real, (size_t)nx * ny * nzl * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+
+  void set_sol(const double* s_host) override {
+    PTF_CUDA(cudaMemcpyAsync(YA.p, s_host, nspec * sizeof(double2), cudaMemcpyHostToDevice, ctx.stream));
+    dim3 grid((nz + 31) / 32, (nkx + 31) / 32, nyl), block(32, 8, 1);
+    k_state_canon<1><<<grid, block, 0, ctx.stream>>>(YA.p, s0.p, nkx, nyl, nz);
+    ++own_launches;
+    ac_valid = false;
+    PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+
+  void get_sol(double* s_host) override {
+    dim3 grid((nz + 31) / 32, (nkx + 31) / 32, nyl), block(32, 8, 1);
+    k_state_canon<0><<<grid, block, 0, ctx.stream>>>(s0.p, YA.p, nkx, nyl, nz);
+    ++own_launches;
+    PTF_CUDA(cudaMemcpyAsync(s_host, YA.p, nspec * sizeof(double2), cudaMemcpyDeviceToHost, ctx.stream));
+    PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+
+  void on_dt_changed() override {
+    drop_graphs();
+    if (ctx.st.base == PTF_STEPPER_ETDRK4) {
+      k_etd_coeffs<<<1184, 256, 0, ctx.stream>>>(cE.p, cE2.p, cZ.p, cA.p, cB.p, cG.p, ctx.ax, nkx, nyl, nz, ctx.dt, 2,
+                                                 g.yoff);
+      ++own_launches;
+      PTF_CUDA(cudaGetLastError());
+    }
+  }
+
+  void enqueue_step(int variant) {
+    static const double LA[5] = {0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                                 -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
+    static const double LB[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
+                                 1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
+                                 2277821191437.0 / 14882151754819.0};
+    switch (ctx.st.base) {
+      case PTF_STEPPER_RK4:
+        stage(CM_RK4_S1); stage(CM_RK4_S2); stage(CM_RK4_S3); stage(CM_RK4_S4);
+        break;
+      case PTF_STEPPER_ETDRK4:
+        stage(CM_ETD_S1); stage(CM_ETD_S2); stage(CM_ETD_S3); stage(CM_ETD_S4);
+        break;
+      case PTF_STEPPER_FORWARD_EULER:
+        stage(CM_EULER);
+        break;
+      case PTF_STEPPER_LSRK54:
+        for (int i = 0; i < 5; ++i) stage(CM_LSRK, LA[i], LB[i], i == 4);
+        break;
+      case PTF_STEPPER_AB3:
+        stage(variant == 1 ? CM_AB3_EULER : CM_AB3);
+        break;
+    }
+  }
+
+  void step_once(int64_t step_index) override {
+    refresh_separable();
+    if (!ac_valid) prologue();
+    int variant = (ctx.st.base == PTF_STEPPER_AB3 && step_index < 3) ? 1 : 0;
+    if (!ctx.d.use_graph) {
+      enqueue_step(variant);
+      PTF_CUDA(cudaGetLastError());
+      return;
+    }
+    if (!graph_exec[variant]) {
+      int64_t o0 = own_launches, l0 = lib_calls;
+      cudaGraph_t graph = nullptr;
+      PTF_CUDA(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        enqueue_step(variant);
+      } catch (...) {
+        cudaStreamEndCapture(ctx.stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      PTF_CUDA(cudaStreamEndCapture(ctx.stream, &graph));
+      cudaError_t e = cudaGraphInstantiate(&graph_exec[variant], graph, 0);
+      cudaGraphDestroy(graph);
+      PTF_CUDA(e);
+      per_step_own = own_launches - o0;
+      per_step_lib = lib_calls - l0;
+      own_launches = o0;
+      lib_calls = l0;
+    }
+    PTF_CUDA(cudaGraphLaunch(graph_exec[variant], ctx.stream));
+    own_launches += per_step_own;
+    lib_calls += per_step_lib;
+  }
+
+  void drop_graphs() {
+    for (auto& ge : graph_exec) {
+      if (ge) cudaGraphExecDestroy(ge);
+      ge = nullptr;
+    }
+  }
+
+  void diag(double* mean_c, double* var_c, double* max_abs_sol) override {
+    DevBuf<double> out;
+    out.alloc(4);
+    PTF_CUDA(cudaMemsetAsync(out.p, 0, 4 * sizeof(double), ctx.stream));
+    k_diag_t<<<1184, 256, 0, ctx.stream>>>(s0.p, nkx, (int64_t)nyl * nz, 1, nx, out.p);
+    ++own_launches;
+    PTF_CUDA(cudaMemcpyAsync(out.p + 2, s0.p, sizeof(double2), cudaMemcpyDeviceToDevice, ctx.stream));  // DC mode
+#ifdef PTF_WITH_NCCL
+    if (P > 1) {  // spectral rows are spread over the ranks; the DC mode lives on rank 0
+      ncclComm_t comm = (ncclComm_t)ctx.nccl_comm;
+      ncclAllReduce(out.p, out.p, 1, ncclDouble, ncclSum, comm, ctx.stream);
+      ncclAllReduce(out.p + 1, out.p + 1, 1, ncclDouble, ncclMax, comm, ctx.stream);
+      ncclBroadcast(out.p + 2, out.p + 2, 2, ncclDouble, 0, comm, ctx.stream);
+    }
+#endif
+    double h[4];
+    PTF_CUDA(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+    PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+    double N = (double)g.npts();
+    double m = h[2] / N;
+    double msq = h[0] / (N * N);
+    if (mean_c) *mean_c = m;
+    if (var_c) *var_c = msq - m * m;
+    if (max_abs_sol) *max_abs_sol = std::sqrt(h[1]);
+  }
+
+  // Average device time of one of the four stage kernels over `reps` REAL RK4 steps (events around every launch of
+  // that kernel on the step stream).  The solution is backed up and restored, the clock is untouched.
+  float time_kernel(const char* kname, int reps) override {
+    std::string k(kname ? kname : "");
+    int which = k == "zkernel" ? 0 : k == "yinv" ? 1 : k == "xkernel" ? 2 : k == "yfwd" ? 3 : -1;
+    if (which < 0) throw Error(PTF_EINVAL, "fused 3-D engine: unknown kernel '" + k + "' (zkernel|yinv|xkernel|yfwd)");
+    if (ctx.st.base != PTF_STEPPER_RK4) throw Error(PTF_EUNSUPPORTED, "kernel timing is implemented for RK4 steps");
+    DevBuf<double2> backup;
+    backup.alloc(nspec);
+    PTF_CUDA(cudaMemcpyAsync(backup.p, s0.p, s0.bytes(), cudaMemcpyDeviceToDevice, ctx.stream));
+    refresh_separable();
+    if (!ac_valid) prologue();
+    const int modes[4] = {CM_RK4_S1, CM_RK4_S2, CM_RK4_S3, CM_RK4_S4};
+    std::vector<cudaEvent_t> ev(2 * 4 * reps);
+    for (auto& e : ev) PTF_CUDA(cudaEventCreate(&e));
+    auto one_step = [&](int rep, bool record) {
+      for (int s = 0; s < 4; ++s) {
+        int idx = 2 * (4 * rep + s);
+        auto timed = [&](int id, auto&& fn) {
+          if (record && which == id) PTF_CUDA(cudaEventRecord(ev[idx], ctx.stream));
+          fn();
+          if (record && which == id) PTF_CUDA(cudaEventRecord(ev[idx + 1], ctx.stream));
+        };
+        timed(1, [&] { run_yinv(); });
+        timed(2, [&] { run_x(); });
+        timed(3, [&] { run_yfwd(); });
+        exchange(PXY, RP);
+        timed(0, [&] { run_z(true, modes[s]); });
+        exchange(ZA, RA);
+        exchange(ZC, RC);
+      }
+    };
+    one_step(0, false);  // warm
+    for (int r = 0; r < reps; ++r) one_step(r, true);
+    PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+    double total = 0;
+    for (int i = 0; i < 4 * reps; ++i) {
+      float ms = 0;
+      PTF_CUDA(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+      total += ms;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    PTF_CUDA(cudaMemcpyAsync(s0.p, backup.p, s0.bytes(), cudaMemcpyDeviceToDevice, ctx.stream));
+    ac_valid = false;
+    PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+    return (float)(total / (4.0 * reps));
+  }
+
+ private:
+  Context& ctx;
+  Geometry& g;
+  int nx, ny, nz, nkx, nyl, nzl, P, rank;
+  size_t nspec, blk;
+  DevBuf<double2> s0, s1, s2, acc, n1, U1, U2, U3, U4, YA, YB, YC;
+  double2 *ZA = nullptr, *ZC = nullptr, *RA = nullptr, *RC = nullptr, *PX = nullptr, *PXY = nullptr, *RP = nullptr;
+  DevBuf<double> cE, cE2, cZ, cA, cB, cG;
+  TwiddleSet twx, twy_own, twz_own;
+  VelocityStore vs;
+  DevBuf<double> sepv[3];   // separable flows: u, v, w of the current step (local planes)
+  bool sep_dirty = true;
+  cufftHandle plan_fwd = 0, plan_inv = 0;
+  bool ac_valid = false;
+  int n_sm = 148;
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+  int64_t per_step_own = 0, per_step_lib = 0;
+};
+
+}  // namespace
+
+bool fused3d_engine_supports(const Context& ctx, std::string* why) {
+  auto no = [&](const char* m) {
+    if (why) *why = m;
+    return false;
+  };
+  const Geometry& g = ctx.g;
+  if (g.ndim != 3) return no("not a 3-D problem");
+  if (!is_fused3_size(g.nx) || !is_fused3_size(g.ny) || !is_fused3_size(g.nz))
+    return no("nx, ny and nz must be powers of two in [64, 1024]");
+  if (g.B != 1) return no("3-D ensembles run on the cuFFT engine");
+  if (ctx.d.flow_kind == PTF_FLOW_EXPR) return no("expression flows (PTF_FLOW_EXPR) run on the cuFFT pipelines");
+  if (ctx.d.flow_kind == PTF_FLOW_LAYERED) return no("layered flows are 2-D per layer");
+  const int P = g.slab ? g.P : 1;
+  if ((P & (P - 1)) || P > 16) return no("the number of ranks must be a power of two, at most 16");
+  if (g.nzl < 8 || g.nyl < 1) return no("each rank needs at least 8 z planes");
+  return true;
+}
+
+std::unique_ptr<Engine> make_fused3d_engine(Context& ctx) {
+  std::string why;
+  if (!fused3d_engine_supports(ctx, &why)) throw Error(PTF_EUNSUPPORTED, "fused 3-D engine: " + why);
+  return std::unique_ptr<Engine>(new Fused3DEngine(ctx));
+}
+
+}  // namespace ptf

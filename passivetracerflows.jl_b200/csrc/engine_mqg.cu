@@ -774,6 +774,7 @@ struct ptf_mqg_handle {
   std::vector<double> H, b, U, eta;   // owned copies of the descriptor's arrays
   std::vector<ptf_handle*> tracers;   // coupled tracer problems (their velocity pointers alias this solver's u, v)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_flow = nullptr, ev_tracer = nullptr;   // cross-stream ordering when a coupled tracer runs on another stream
 };
 
 namespace {
@@ -883,6 +884,8 @@ int32_t ptf_mqg_create(const ptf_mqg_desc* d, ptf_mqg_handle** out) {
     h->solver.reset(new ptf::MqgSolver(dd));
     PTF_CUDA(cudaEventCreate(&h->ev0));
     PTF_CUDA(cudaEventCreate(&h->ev1));
+    PTF_CUDA(cudaEventCreateWithFlags(&h->ev_flow, cudaEventDisableTiming));
+    PTF_CUDA(cudaEventCreateWithFlags(&h->ev_tracer, cudaEventDisableTiming));
   } catch (const ptf::Error& e) {
     g_mqg_create_error = e.what();
     return e.code;
@@ -908,6 +911,8 @@ int32_t ptf_mqg_destroy(ptf_mqg_handle* h) {
   h->solver.reset();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_flow) cudaEventDestroy(h->ev_flow);
+  if (h->ev_tracer) cudaEventDestroy(h->ev_tracer);
   delete h;
   return PTF_OK;
 }
@@ -1061,9 +1066,21 @@ int32_t ptf_mqg_step_coupled(ptf_mqg_handle* m, ptf_handle* tracer, int64_t nste
     bool known = false;
     for (ptf_handle* t : m->tracers) known = known || (t == tracer);
     PTF_REQUIRE(known, "ptf_mqg_step_coupled: the tracer is not coupled to this flow (ptf_mqg_couple)");
+    // The flow runs on the stream of the tracer that coupled LAST; any other coupled tracer has its own stream and
+    // reads the flow's u, v buffers from there: order the two streams explicitly in that case.
+    cudaStream_t ts = ptf::tracer_stream(tracer);
+    const bool cross = ts != s.stream;
     PTF_CUDA(cudaEventRecord(m->ev0, s.stream));
     for (int64_t i = 0; i < nsteps; ++i) {
+      if (cross) {   // the tracer's product kernels must see the u, v of the flow's last updatevars!
+        PTF_CUDA(cudaEventRecord(m->ev_flow, s.stream));
+        PTF_CUDA(cudaStreamWaitEvent(ts, m->ev_flow, 0));
+      }
       ptf::tracer_step_one(tracer);
+      if (cross) {   // ... and the flow must not overwrite them (calcN_advection! uses vars.u, vars.v as scratch) before
+        PTF_CUDA(cudaEventRecord(m->ev_tracer, ts));   // the tracer step has read them
+        PTF_CUDA(cudaStreamWaitEvent(s.stream, m->ev_tracer, 0));
+      }
       s.steps(1);
       s.updatevars(i + 1 == nsteps);   // intermediate iterations only need u, v (the tracer's inputs)
     }

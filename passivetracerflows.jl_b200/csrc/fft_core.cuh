@@ -1,6 +1,7 @@
 // Hand-written fp64 complex FFT for one CTA sub-group: N = 256*R3 points (R3 in {1,2,4,8,16}), T = N/16 threads,
 // 16 elements per thread held in registers, Stockham autosort passes radix 16 -> 16 -> R3 with padded
-// shared-memory exchanges between them.
+// shared-memory exchanges between them.  N = 64 and 128 (the reference's default grid size, TAD.jl:144,166) run two
+// passes, radix 16 -> N/16, with one exchange.
 //
 // Thread <-> data contract (both on entry and on exit):  thread t holds element  t + T*e  in logical slot e.
 //   * on entry  v[e]            = x[t + T*e]            (natural slots)
@@ -103,19 +104,31 @@ PTF_HD void dft8(double2& x0, double2& x1, double2& x2, double2& x3, double2& x4
 
 PTF_HD constexpr int pad_idx(int i) { return i + (i >> 4); }
 
+#ifdef __CUDACC__
+// Value barrier for the optimiser: the result is "a different value" as far as common-subexpression elimination and
+// loop-invariant code motion can tell.  Used on gather strides / bases so that 16 precomputed 64-bit addresses are
+// not kept live across a transform (32 registers = spills at 128 registers per thread); recomputing them is 1 IMAD each.
+__device__ __forceinline__ size_t opaque(size_t x) {
+  asm volatile("" : "+l"(x));
+  return x;
+}
+#endif
+
 // Device-resident twiddle tables for one transform length (forward sign; inverse conjugates on use).
 struct Twiddles {
-  const double2* tw2;  // [4][16]    w_256^(2^m * k), m = 0..3, k = 0..15
-  const double2* tw3;  // [4][256]   w_N^(2^m * k), m = 0..3, k = 0..255   (unused for N = 256)
+  const double2* tw2;  // [4][16]    N >= 256: w_256^(2^m * k);  N < 256: w_N^(2^m * k);  m = 0..3, k = 0..15
+  const double2* tw3;  // [4][256]   w_N^(2^m * k), m = 0..3, k = 0..255   (unused for N <= 256)
 };
 
 template <int N>
 struct Cfg {
   static constexpr int T = N / 16;     // threads per transform
-  static constexpr int R3 = N / 256;   // radix of the third pass (1 = no third pass)
-  static constexpr int S = (R3 > 0) ? 16 / R3 : 16;  // work items per thread in the third pass
+  static constexpr bool TWO_PASS = N < 256;            // radix 16 -> N/16
+  static constexpr int R3 = TWO_PASS ? N / 16 : N / 256;  // radix of the LAST pass (1 = no last pass, N = 256)
+  static constexpr int S = (R3 > 0) ? 16 / R3 : 16;  // work items per thread in the last pass
   static constexpr int PADN = N + N / 16;
-  static_assert(N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096, "unsupported FFT length");
+  static_assert(N == 64 || N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096,
+                "unsupported FFT length");
 };
 
 // logical element e (index t + T*e) -> register slot, after the transform
@@ -150,11 +163,61 @@ PTF_HD void twiddle15(double2 (&v)[16], double2 w1, double2 w2, double2 w4, doub
 }
 
 #ifdef __CUDACC__
-// One transform by T cooperating threads of a CTA; all 256 threads of the CTA must call it (CTA-wide barriers).
-// `sm` points at this transform's padded buffer; it may be reused by the caller after the call returns AND a barrier.
-template <int N, int DIR>
-__device__ __forceinline__ void fft_cta(double2 (&v)[16], double2* __restrict__ sm, int t, const Twiddles& tw) {
+// Last Stockham pass: radix R3 over sub-transforms of length NS (= N / R3); work item q of thread t is element
+// j = t + q*T, uses register slots q + r*S, twiddles w_N^(r*k) with k = j mod NS read from tab[m*NS + k] = w_N^(2^m k).
+template <int N, int DIR, int NS>
+__device__ __forceinline__ void last_pass(double2 (&v)[16], int t, const double2* __restrict__ tab) {
   constexpr int T = Cfg<N>::T, R3 = Cfg<N>::R3, S = Cfg<N>::S;
+#pragma unroll
+  for (int q = 0; q < S; ++q) {
+    const int k = (t + q * T) & (NS - 1);
+    double2 w1 = __ldg(&tab[k]);
+    if (R3 == 2) {
+      v[q + S] = twmul<DIR>(v[q + S], w1);
+      dft2(v[q], v[q + S]);
+    } else if (R3 == 4) {
+      double2 w2 = __ldg(&tab[NS + k]);
+      double2 w3 = cmul2(w1, w2);
+      v[q + S] = twmul<DIR>(v[q + S], w1);
+      v[q + 2 * S] = twmul<DIR>(v[q + 2 * S], w2);
+      v[q + 3 * S] = twmul<DIR>(v[q + 3 * S], w3);
+      dft4<DIR>(v[q], v[q + S], v[q + 2 * S], v[q + 3 * S]);
+    } else if (R3 == 8) {
+      double2 w2 = __ldg(&tab[NS + k]);
+      double2 w4 = __ldg(&tab[2 * NS + k]);
+      double2 w3 = cmul2(w1, w2), w5 = cmul2(w4, w1), w6 = cmul2(w4, w2);
+      double2 w7 = cmul2(w4, w3);
+      v[q + S] = twmul<DIR>(v[q + S], w1);
+      v[q + 2 * S] = twmul<DIR>(v[q + 2 * S], w2);
+      v[q + 3 * S] = twmul<DIR>(v[q + 3 * S], w3);
+      v[q + 4 * S] = twmul<DIR>(v[q + 4 * S], w4);
+      v[q + 5 * S] = twmul<DIR>(v[q + 5 * S], w5);
+      v[q + 6 * S] = twmul<DIR>(v[q + 6 * S], w6);
+      v[q + 7 * S] = twmul<DIR>(v[q + 7 * S], w7);
+      dft8<DIR>(v[q], v[q + S], v[q + 2 * S], v[q + 3 * S], v[q + 4 * S], v[q + 5 * S], v[q + 6 * S], v[q + 7 * S]);
+    } else {  // R3 == 16 (S == 1, q == 0)
+      double2 w2 = __ldg(&tab[NS + k]);
+      double2 w4 = __ldg(&tab[2 * NS + k]);
+      double2 w8 = __ldg(&tab[3 * NS + k]);
+      twiddle15<DIR>(v, w1, w2, w4, w8);
+      dft16<DIR>(v);
+    }
+  }
+}
+
+// One transform by T cooperating threads of a CTA; all threads of the CTA must call it (CTA-wide barriers).
+// `sm` points at this transform's padded buffer; it may be reused by the caller after the call returns AND a barrier.
+// OPAQUE_TW: hide the twiddle-table pointers from the optimiser for this call.  A kernel that runs several transforms
+// of the same length back to back otherwise gets their (identical) twiddle loads merged and kept live across the
+// transforms in between: up to 48 registers, i.e. spills at 128 registers per thread.
+template <int N, int DIR, bool OPAQUE_TW = false>
+__device__ __forceinline__ void fft_cta(double2 (&v)[16], double2* __restrict__ sm, int t, const Twiddles& tw_in) {
+  constexpr int T = Cfg<N>::T, R3 = Cfg<N>::R3;
+  Twiddles tw = tw_in;
+  if (OPAQUE_TW) {
+    asm volatile("" : "+l"(tw.tw2));
+    asm volatile("" : "+l"(tw.tw3));
+  }
   // ---- pass 1: radix 16, Ns = 1, no twiddles ----
   dft16<DIR>(v);
   __syncthreads();  // buffer free (previous readers done)
@@ -163,6 +226,10 @@ __device__ __forceinline__ void fft_cta(double2 (&v)[16], double2* __restrict__ 
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
+  if (Cfg<N>::TWO_PASS) {  // N = 64, 128: last pass radix N/16 over the 16-point sub-transforms
+    last_pass<N, DIR, 16>(v, t, tw.tw2);
+    return;
+  }
   // ---- pass 2: radix 16, Ns = 16 ----
   const int k2 = t & 15;
   {
@@ -182,42 +249,8 @@ __device__ __forceinline__ void fft_cta(double2 (&v)[16], double2* __restrict__ 
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
-  // ---- pass 3: radix R3, Ns = 256; work item q uses slots q + r*S ----
-#pragma unroll
-  for (int q = 0; q < S; ++q) {
-    const int k = (t + q * T) & 255;
-    double2 w1 = __ldg(&tw.tw3[k]);
-    if (R3 == 2) {
-      v[q + S] = twmul<DIR>(v[q + S], w1);
-      dft2(v[q], v[q + S]);
-    } else if (R3 == 4) {
-      double2 w2 = __ldg(&tw.tw3[256 + k]);
-      double2 w3 = cmul2(w1, w2);
-      v[q + S] = twmul<DIR>(v[q + S], w1);
-      v[q + 2 * S] = twmul<DIR>(v[q + 2 * S], w2);
-      v[q + 3 * S] = twmul<DIR>(v[q + 3 * S], w3);
-      dft4<DIR>(v[q], v[q + S], v[q + 2 * S], v[q + 3 * S]);
-    } else if (R3 == 8) {
-      double2 w2 = __ldg(&tw.tw3[256 + k]);
-      double2 w4 = __ldg(&tw.tw3[512 + k]);
-      double2 w3 = cmul2(w1, w2), w5 = cmul2(w4, w1), w6 = cmul2(w4, w2);
-      double2 w7 = cmul2(w4, w3);
-      v[q + S] = twmul<DIR>(v[q + S], w1);
-      v[q + 2 * S] = twmul<DIR>(v[q + 2 * S], w2);
-      v[q + 3 * S] = twmul<DIR>(v[q + 3 * S], w3);
-      v[q + 4 * S] = twmul<DIR>(v[q + 4 * S], w4);
-      v[q + 5 * S] = twmul<DIR>(v[q + 5 * S], w5);
-      v[q + 6 * S] = twmul<DIR>(v[q + 6 * S], w6);
-      v[q + 7 * S] = twmul<DIR>(v[q + 7 * S], w7);
-      dft8<DIR>(v[q], v[q + S], v[q + 2 * S], v[q + 3 * S], v[q + 4 * S], v[q + 5 * S], v[q + 6 * S], v[q + 7 * S]);
-    } else {  // R3 == 16 (S == 1, q == 0)
-      double2 w2 = __ldg(&tw.tw3[256 + k]);
-      double2 w4 = __ldg(&tw.tw3[512 + k]);
-      double2 w8 = __ldg(&tw.tw3[768 + k]);
-      twiddle15<DIR>(v, w1, w2, w4, w8);
-      dft16<DIR>(v);
-    }
-  }
+  // ---- pass 3: radix R3, Ns = 256 ----
+  last_pass<N, DIR, 256>(v, t, tw.tw3);
 }
 #endif  // __CUDACC__
 

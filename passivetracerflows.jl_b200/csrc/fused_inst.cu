@@ -3,7 +3,7 @@
 #ifndef PTF_INST_N
 #error "compile with -DPTF_INST_N=<transform length>"
 #endif
-#include "fused_kernels.cuh"
+#include "fused3d_kernels.cuh"
 
 #define PTF_CAT2(a, b) a##b
 #define PTF_CAT(a, b) PTF_CAT2(a, b)
@@ -23,6 +23,20 @@ void FN(fused_launch_y_)(bool has_in, int fam, const void* yargs, int nb, cudaSt
 void FN(fused_launch_x_)(int vmode, const void* xargs, int nb, cudaStream_t st, int n_sm) {
   launch_x<PTF_INST_N>(vmode, *static_cast<const XArgs*>(xargs), nb, st, n_sm);
 }
+
+// ---- fused 3-D engine (engine_fused3d.cu): transform lengths up to 1024 per axis ----
+#if PTF_INST_N <= 1024
+void FN(fused3_prep_)() { prep3<PTF_INST_N>(); }
+void FN(fused3_launch_z_)(bool has_in, int fam, const void* yargs, cudaStream_t st, int n_sm) {
+  launch_z3<PTF_INST_N>(has_in, fam, *static_cast<const YArgs*>(yargs), st, n_sm);
+}
+void FN(fused3_launch_x_)(int vmode, const void* xargs, int nplanes, cudaStream_t st, int n_sm) {
+  launch_x3<PTF_INST_N>(vmode, *static_cast<const XArgs*>(xargs), nplanes, st, n_sm);
+}
+void FN(fused3_launch_y_)(bool inverse, const void* y3args, cudaStream_t st, int n_sm) {
+  launch_y3<PTF_INST_N>(inverse, *static_cast<const Y3Args*>(y3args), st, n_sm);
+}
+#endif
 
 // transform self-test + the timing experiments recorded in profiles/r01_fft_core_experiments.md
 void FN(fused_selftest_)(int dir, int count, const double2* in, double2* out, const void* twp) {

@@ -45,14 +45,18 @@ struct YArgs {
   CombineArgs C;
   AxisTables ax;
   Twiddles tw;
-  int nkr;
-  double inv_n;               // 1/(nx*ny): normalisation of ldiv!(., rfftplan, .)
+  int nkr;                    // number of columns per member (2-D: nx/2+1;  3-D: (nx/2+1) * nyl)
+  double inv_n;               // 1/(nx*ny[*nz]): normalisation of ldiv!(., rfftplan, .)
   const double2* pf_c[4];     // complex state columns the combine will read: L2-prefetched at CTA start
   const double* pf_r[4];      // real coefficient columns (ETDRK4), same
   int pf_ahead;               // > 0: also prefetch the P^x gather of the column `pf_ahead` CTAs ahead
   int ablate;                 // experiment bitmask (timing only): 1 = contiguous instead of gathered P^x
   int stagger;                // first-wave de-phasing: odd CTAs of the first wave start `stagger` cycles late
   int first_wave;             // number of CTAs resident at launch (2 per SM)
+  // ---- 3-D (template parameter D3): this kernel is the z-column kernel, one column per (kr, local ky row) ----
+  int nkx = 0;                // nx/2+1
+  int nyl = 1, yoff = 0;      // local ky rows of this rank's spectral slab and the global index of the first one
+  int nzl = 0, zsh = 0;       // planes per rank (nz / P, a power of two) and log2 of it
 };
 
 enum { FAM_RK4 = 0, FAM_ETD = 1, FAM_OTHER = 2 };
@@ -60,22 +64,44 @@ enum { FAM_RK4 = 0, FAM_ETD = 1, FAM_OTHER = 2 };
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // FourierFlows filter, out of line: sqrt/exp/pow would otherwise be inlined once per register element
-__device__ __noinline__ double filter_slow(double fx, double fy, double f_inner, double f_decay, double f_order,
-                                           double kx, double ky) {
-  double a = kx * fx, b = ky * fy;
-  double K = sqrt(a * a + b * b);
+// (a, b, c = k_axis * d_axis / pi per axis; c = 0 in 2-D)
+__device__ __noinline__ double filter_slow(double a, double b, double c, double f_inner, double f_decay,
+                                           double f_order) {
+  double Ksq = a * a;
+  Ksq += b * b;
+  Ksq += c * c;
+  double K = sqrt(Ksq);
   if (K < f_inner) return 1.0;
   return exp(-f_decay * pow(K - f_inner, f_order));
 }
 
+// One column of the column kernel: 2-D = (kr; transform axis y), 3-D = (kr, ky row lp; transform axis z).
+// ka = wavenumber along the transform axis.
+template <bool D3>
+__device__ __forceinline__ double col_lin(const AxisTables& ax, double kx, double kyp, double ka) {
+  return D3 ? lin_op(ax, kx, kyp, ka) : lin_op(ax, kx, ka, 0.0);
+}
+template <bool D3>
+__device__ __forceinline__ bool col_dealiased(const AxisTables& ax, int kr, int lp, int l) {
+  return D3 ? dealiased_out(ax, kr, lp, l) : dealiased_out(ax, kr, l, 0);
+}
+struct ColId {
+  int kr, lp;        // kr index; 3-D: GLOBAL ky index of this column (0 in 2-D)
+  double kx, kyp;    // their wavenumbers
+  const double* kax; // wavenumber table of the transform axis
+};
+
 // ---- RK4 family (FF RK4substeps!/RK4update!).  N^ (t_nh) and the new stage state s' (t_w) live in TMEM, so a
 // ---- batch of NB elements can have all 3*NB of its 16-byte state loads in flight at once (2 memory round trips
 // ---- per column instead of 4) and nothing accumulates in registers.
-template <int NY, int MODE, bool DM>
-__device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_t t_w, size_t col, int t, double kx,
-                                          bool active, const double (&fl)[16], int kr) {
+// FILT: the final stage applies the FourierFlows filter (compiled out otherwise: `fl` is a run-time indexed array in
+// local memory, and an unfiltered RK4 step must not pay 16 local loads per thread for it)
+template <int NY, int MODE, bool DM, bool FILT, bool D3>
+__device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_t t_w, size_t col, int t,
+                                          const ColId& c, bool active, const double (&fl)[16]) {
   constexpr int T = Cfg<NY>::T, NB = 4;
   const double dt = a.C.dt;
+  const double kx = c.kx;
 #pragma unroll
   for (int e0 = 0; e0 < 16; e0 += NB) {
     double2 ss[NB], s0[NB], ac[NB];
@@ -84,7 +110,7 @@ __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_
       const size_t i = col + t + T * (e0 + j);
       s0[j] = __ldcg(a.P.s0 + i);
       // opt-in dealias!(sol) at the top of calcN: sol is read as if it had been masked in place at stage 1
-      if (DM && dealiased_out(a.ax, kr, t + T * (e0 + j), 0)) s0[j] = make_double2(0.0, 0.0);
+      if (DM && col_dealiased<D3>(a.ax, c.kr, c.lp, t + T * (e0 + j))) s0[j] = make_double2(0.0, 0.0);
       if (MODE != CM_RK4_S1) {
         ss[j] = __ldcg(a.P.s1 + i);
         ac[j] = __ldcg(a.P.acc + i);
@@ -98,10 +124,9 @@ __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_
       for (int jj = 0; jj < 4; ++jj) {
         const int j = j0 + jj, e = e0 + j, l = t + T * e;
         const size_t i = col + l;
-        const double ky = a.ax.ky[l];
-        const double L = lin_op(a.ax, kx, ky, 0.0);
+        const double L = col_lin<D3>(a.ax, kx, c.kyp, c.kax[l]);
         const double2 Nh = nh[jj];
-        const bool dm = DM && dealiased_out(a.ax, kr, l, 0);
+        const bool dm = DM && col_dealiased<D3>(a.ax, c.kr, c.lp, l);
         double2 next;
         if (MODE == CM_RK4_S1) {
           double2 k = cadd(Nh, cmul_r(s0[j], L));
@@ -123,7 +148,7 @@ __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_
           double2 k = cadd(Nh, cmul_r(ss[j], L));
           double2 sum = cadd(ac[j], cmul_r(k, 1.0 / 6.0));
           next = cadd(s0[j], cmul_r(sum, dt));
-          if (a.C.filtered) next = cmul_r(next, fl[e]);
+          if (FILT) next = cmul_r(next, fl[e]);
           if (active) __stcg(a.P.s0 + i, next);  // stored unmasked (as the reference leaves sol after the update) ...
           if (dm) next = make_double2(0.0, 0.0); // ... but the next step's first calcN sees it masked
         }
@@ -135,9 +160,9 @@ __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_
 }
 
 // ---- ETDRK4 family (FF ETDRK4substeps!/ETDRK4update!)
-template <int NY, int MODE, bool DM>
+template <int NY, int MODE, bool DM, bool FILT, bool D3>
 __device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16], double2 (&w)[16], size_t col,
-                                          size_t ccol, int t, double kx, bool active, const double (&fl)[16], int kr) {
+                                          size_t ccol, int t, const ColId& c, bool active, const double (&fl)[16]) {
   constexpr int T = Cfg<NY>::T, NB = 4;
 #pragma unroll
   for (int e0 = 0; e0 < 16; e0 += NB) {
@@ -146,7 +171,7 @@ __device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16]
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       const size_t i = col + t + T * (e0 + j), ci = ccol + t + T * (e0 + j);
-      const bool dmj = DM && dealiased_out(a.ax, kr, t + T * (e0 + j), 0);
+      const bool dmj = DM && col_dealiased<D3>(a.ax, c.kr, c.lp, t + T * (e0 + j));
       if (MODE == CM_ETD_S1 || MODE == CM_ETD_S2) {
         sa[j] = __ldcg(a.P.s0 + i);
         if (dmj) sa[j] = make_double2(0.0, 0.0);
@@ -174,7 +199,7 @@ __device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16]
       const int e = e0 + j, l = t + T * e;
       const size_t i = col + l;
       const double2 Nh = v[out_slot<NY>(e)];
-      const bool dm = DM && dealiased_out(a.ax, kr, l, 0);
+      const bool dm = DM && col_dealiased<D3>(a.ax, c.kr, c.lp, l);
       double2 next;
       if (MODE == CM_ETD_S1) {
         next = cadd(cmul_r(sa[j], c0[j]), cmul_r(Nh, c1[j]));
@@ -203,7 +228,7 @@ __device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16]
         r = cadd(r, cmul_r(n1[j], c1[j]));
         r = cadd(r, cmul_r(ac[j], 2 * c2[j]));
         r = cadd(r, cmul_r(Nh, c3[j]));
-        if (a.C.filtered) r = cmul_r(r, fl[e]);
+        if (FILT) r = cmul_r(r, fl[e]);
         next = r;
         if (active) __stcg(a.P.s0 + i, next);
         if (dm) next = make_double2(0.0, 0.0);
@@ -216,7 +241,10 @@ __device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16]
 // NT = threads per CTA (64, 128 or 256; >= T).  Small problems use small CTAs so that enough CTAs exist to fill the
 // 148 SMs; TMEM is allocated 128 columns per warp-quarter, i.e. 128 columns per CTA up to 4 warps, 256 for 8 warps.
 // DM = the opt-in dealias!(sol) mask is compiled in (kept out of the default kernels: it costs registers)
-template <int NY, int FAM, bool HAS_IN, bool HAS_OUT, int NT, bool DM = false>
+// D3 = z-column kernel of the fused 3-D engine (engine_fused3d.cu): column = (kr, local ky row), transform axis z,
+//      input P^xy gathered from [r][kr][zl/8][ll][zl%8] (r = z / nzl: the block received from rank r), outputs
+//      A = IFFT_z(s'), C = IFFT_z(i*m*s') written as [p][kr][ll][zl] (p = z / nzl: the block sent to rank p).
+template <int NY, int FAM, bool HAS_IN, bool HAS_OUT, int NT, bool DM = false, bool D3 = false>
 __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
   constexpr int T = Cfg<NY>::T, F = NT / T, PADN = Cfg<NY>::PADN;
   constexpr int TCOLS = NT > 128 ? 256 : 128;
@@ -239,31 +267,60 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
     t_w = t_nh + 64;
   }
   const int grp = threadIdx.x / T, t = threadIdx.x % T;
-  const int kr_raw = blockIdx.x * F + grp;
-  const bool active = kr_raw < a.nkr;
-  const int kr = active ? kr_raw : 0;
+  const int cid_raw = blockIdx.x * F + grp;
+  const bool active = cid_raw < a.nkr;
+  const int cid = active ? cid_raw : 0;
   const int b = blockIdx.y;
   double2* sm = smem + grp * PADN;
-  const size_t col = ((size_t)b * a.nkr + kr) * NY;  // this column in the transposed state arrays
-  const size_t ccol = (size_t)kr * NY;               // ... in the batch-shared coefficient arrays
-  const double kx = a.ax.kx[kr];
+  const size_t col = ((size_t)b * a.nkr + cid) * NY;  // this column in the transposed state arrays
+  const size_t ccol = (size_t)cid * NY;               // ... in the batch-shared coefficient arrays
+  ColId c;
+  int ll = 0;                                         // 3-D: local ky row
+  if (D3) {
+    c.kr = cid / a.nyl;
+    ll = cid - c.kr * a.nyl;
+    c.lp = a.yoff + ll;
+    c.kyp = a.ax.ky[c.lp];
+    c.kax = a.ax.kz;
+  } else {
+    c.kr = cid;
+    c.lp = 0;
+    c.kyp = 0.0;
+    c.kax = a.ax.ky;
+  }
+  c.kx = a.ax.kx[c.kr];
+  const double kx = c.kx;
   double2 w[16];
   double fl[16];  // FourierFlows filter of this thread's 16 modes (final stage of Filtered* steppers only)
   if (HAS_IN && FAM != FAM_OTHER && a.C.filtered && (a.C.mode == CM_RK4_S4 || a.C.mode == CM_ETD_S4)) {
 #pragma unroll 1
-    for (int e = 0; e < 16; ++e)
-      fl[e] = filter_slow(a.ax.fx, a.ax.fy, a.ax.f_inner, a.ax.f_decay, a.ax.f_order, kx, a.ax.ky[t + T * e]);
+    for (int e = 0; e < 16; ++e) {
+      const double ka = c.kax[t + T * e];
+      fl[e] = D3 ? filter_slow(kx * a.ax.fx, c.kyp * a.ax.fy, ka * a.ax.fz, a.ax.f_inner, a.ax.f_decay, a.ax.f_order)
+                 : filter_slow(kx * a.ax.fx, ka * a.ax.fy, 0.0, a.ax.f_inner, a.ax.f_decay, a.ax.f_order);
+    }
   }
 
   if (HAS_IN) {
     double2 v[16];
-    // P^x is stored blocked, [b][y/8][kr][y%8]: 8 consecutive y of one column are one 128-byte line, so this column
-    // read is fully coalesced (the row kernel pays with 32-byte full-sector stores, which do not stall its warps)
-    const double2* P = a.Px + (size_t)b * NY * a.nkr + (size_t)kr * 8;
+    if (D3) {
+      // P^xy blocks as received: [r][kr][zl/8][ll][zl%8]; 8 consecutive z of one column are one 128-byte line
+      const size_t blk = (size_t)a.nkx * (a.nzl >> 3) * a.nyl * 8;   // one rank's block
+      const double2* P = a.Px + ((size_t)c.kr * (a.nzl >> 3) * a.nyl + ll) * 8;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const int y = t + T * e;
-      v[e] = __ldcg((a.ablate & 1) ? (a.Px + col + y) : (P + (size_t)(y >> 3) * a.nkr * 8 + (y & 7)));  // L2-only
+      for (int e = 0; e < 16; ++e) {
+        const int z = t + T * e, r = z >> a.zsh, zl = z & (a.nzl - 1);
+        v[e] = __ldcg(P + (size_t)r * blk + (size_t)(zl >> 3) * a.nyl * 8 + (zl & 7));
+      }
+    } else {
+      // P^x is stored blocked, [b][y/8][kr][y%8]: 8 consecutive y of one column are one 128-byte line, so this
+      // column read is fully coalesced (the row kernel pays with 32-byte full-sector stores, which do not stall it)
+      const double2* P = a.Px + (size_t)b * NY * a.nkr + (size_t)cid * 8;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int y = t + T * e;
+        v[e] = __ldcg((a.ablate & 1) ? (a.Px + col + y) : (P + (size_t)(y >> 3) * a.nkr * 8 + (y & 7)));  // L2-only
+      }
     }
     // Pull the state columns the combine needs into L2 while the gather + forward FFT run (fire and forget).
     if ((t & 7) == 0) {
@@ -283,8 +340,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
         }
     }
     fft::fft_cta<NY, -1>(v, sm, t, a.tw);
-    if (a.pf_ahead > 0) {  // next wave's gather: one 32-byte sector per (y, kr') pair
-      const int kr2 = kr_raw + a.pf_ahead * F;
+    if (!D3 && a.pf_ahead > 0) {  // next wave's gather: one 32-byte sector per (y, kr') pair
+      const int kr2 = cid_raw + a.pf_ahead * F;
       if (kr2 < a.nkr) {
         const double2* P2 = a.Px + (size_t)b * NY * a.nkr + (size_t)kr2 * 8;
 #pragma unroll
@@ -296,10 +353,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
       for (int e = 0; e < 16; ++e) tmem::st1(t_nh + 4 * e, v[out_slot<NY>(e)]);
       tmem::wait_st();
       switch (a.C.mode) {
-        case CM_RK4_S1: rk4_stage<NY, CM_RK4_S1, DM>(a, t_nh, t_w, col, t, kx, active, fl, kr); break;
-        case CM_RK4_S2: rk4_stage<NY, CM_RK4_S2, DM>(a, t_nh, t_w, col, t, kx, active, fl, kr); break;
-        case CM_RK4_S3: rk4_stage<NY, CM_RK4_S3, DM>(a, t_nh, t_w, col, t, kx, active, fl, kr); break;
-        default: rk4_stage<NY, CM_RK4_S4, DM>(a, t_nh, t_w, col, t, kx, active, fl, kr); break;
+        case CM_RK4_S1: rk4_stage<NY, CM_RK4_S1, DM, false, D3>(a, t_nh, t_w, col, t, c, active, fl); break;
+        case CM_RK4_S2: rk4_stage<NY, CM_RK4_S2, DM, false, D3>(a, t_nh, t_w, col, t, c, active, fl); break;
+        case CM_RK4_S3: rk4_stage<NY, CM_RK4_S3, DM, false, D3>(a, t_nh, t_w, col, t, c, active, fl); break;
+        default:
+          if (a.C.filtered) rk4_stage<NY, CM_RK4_S4, DM, true, D3>(a, t_nh, t_w, col, t, c, active, fl);
+          else rk4_stage<NY, CM_RK4_S4, DM, false, D3>(a, t_nh, t_w, col, t, c, active, fl);
+          break;
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -310,21 +370,26 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
       }
     } else if (FAM == FAM_ETD) {
       switch (a.C.mode) {
-        case CM_ETD_S1: etd_stage<NY, CM_ETD_S1, DM>(a, v, w, col, ccol, t, kx, active, fl, kr); break;
-        case CM_ETD_S2: etd_stage<NY, CM_ETD_S2, DM>(a, v, w, col, ccol, t, kx, active, fl, kr); break;
-        case CM_ETD_S3: etd_stage<NY, CM_ETD_S3, DM>(a, v, w, col, ccol, t, kx, active, fl, kr); break;
-        default: etd_stage<NY, CM_ETD_S4, DM>(a, v, w, col, ccol, t, kx, active, fl, kr); break;
+        case CM_ETD_S1: etd_stage<NY, CM_ETD_S1, DM, false, D3>(a, v, w, col, ccol, t, c, active, fl); break;
+        case CM_ETD_S2: etd_stage<NY, CM_ETD_S2, DM, false, D3>(a, v, w, col, ccol, t, c, active, fl); break;
+        case CM_ETD_S3: etd_stage<NY, CM_ETD_S3, DM, false, D3>(a, v, w, col, ccol, t, c, active, fl); break;
+        default:
+          if (a.C.filtered) etd_stage<NY, CM_ETD_S4, DM, true, D3>(a, v, w, col, ccol, t, c, active, fl);
+          else etd_stage<NY, CM_ETD_S4, DM, false, D3>(a, v, w, col, ccol, t, c, active, fl);
+          break;
       }
     } else {
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int l = t + T * e;
         double2 nx = make_double2(0.0, 0.0);
-        const bool dm = DM && dealiased_out(a.ax, kr, l, 0);
+        const bool dm = DM && col_dealiased<D3>(a.ax, c.kr, c.lp, l);
         if (active) {
           // ForwardEuler / LSRK54 / AB3 evaluate calcN at sol itself: dealias!(sol) acts in place before the combine
-          if (dm) a.P.s0[col + l] = make_double2(0.0, 0.0);
-          nx = combine_at<CMASK_OTHER>(a.P, a.C, a.ax, col + l, ccol + l, kx, a.ax.ky[l], 0.0, v[out_slot<NY>(e)]);
+          if (dm && a.C.mode != CM_STORE) a.P.s0[col + l] = make_double2(0.0, 0.0);
+          const double ka = c.kax[l];
+          nx = combine_at<CMASK_OTHER>(a.P, a.C, a.ax, col + l, ccol + l, kx, D3 ? c.kyp : ka, D3 ? ka : 0.0,
+                                       v[out_slot<NY>(e)]);
         }
         if (dm) nx = make_double2(0.0, 0.0);
         w[e] = make_double2(nx.x * a.inv_n, nx.y * a.inv_n);
@@ -334,7 +399,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       double2 s = __ldcg(a.next_state + col + t + T * e);
-      if (DM && dealiased_out(a.ax, kr, t + T * e, 0)) s = make_double2(0.0, 0.0);
+      if (DM && col_dealiased<D3>(a.ax, c.kr, c.lp, t + T * e)) s = make_double2(0.0, 0.0);
       w[e] = make_double2(s.x * a.inv_n, s.y * a.inv_n);
     }
   }
@@ -343,12 +408,17 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
     return;
   }
 
+  // where element l of this column goes in A / B: contiguous in 2-D; 3-D: the block of the rank that owns plane l
+  auto out_off = [&](int l) -> size_t {
+    if (D3) return (((size_t)(l >> a.zsh) * a.nkr + cid) << a.zsh) + (l & (a.nzl - 1));
+    return col + l;
+  };
   fft::fft_cta<NY, +1>(w, sm, t, a.tw);
   if (active) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) __stcg(a.A + col + t + T * e, w[out_slot<NY>(e)]);
+    for (int e = 0; e < 16; ++e) __stcg(a.A + out_off(t + T * e), w[out_slot<NY>(e)]);
   }
-  // y-derivative: i*l*s'
+  // derivative along the transform axis: i*l*s'  (3-D: i*m*s')
   if (USE_TMEM) {  // s'/N is still parked in TMEM: no second trip to global memory
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -356,7 +426,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
       tmem::ldn<4>(t_w + 16 * q, r4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double ky = a.ax.ky[t + T * (4 * q + j)];
+        const double ky = c.kax[t + T * (4 * q + j)];
         w[4 * q + j] = make_double2(-ky * r4[j].y, ky * r4[j].x);
       }
     }
@@ -365,15 +435,15 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
     for (int e = 0; e < 16; ++e) {
       const int l = t + T * e;
       double2 s = __ldcg(a.next_state + col + l);
-      if (DM && dealiased_out(a.ax, kr, l, 0)) s = make_double2(0.0, 0.0);
-      double ky = a.ax.ky[l] * a.inv_n;
+      if (DM && col_dealiased<D3>(a.ax, c.kr, c.lp, l)) s = make_double2(0.0, 0.0);
+      double ky = c.kax[l] * a.inv_n;
       w[e] = make_double2(-ky * s.y, ky * s.x);
     }
   }
   fft::fft_cta<NY, +1>(w, sm, t, a.tw);
   if (active) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) __stcg(a.Bf + col + t + T * e, w[out_slot<NY>(e)]);
+    for (int e = 0; e < 16; ++e) __stcg(a.Bf + out_off(t + T * e), w[out_slot<NY>(e)]);
   }
   if (USE_TMEM) tmem::free_cta<TCOLS>(tbase);
 }
@@ -390,6 +460,9 @@ struct XArgs {
   int pf_ahead;  // > 0: L2-prefetch the A,B gather of the row pair `pf_ahead` CTAs ahead
   int ablate;    // experiment bitmask (timing only): 2 = no u,v loads
   int stagger, first_wave;  // see YArgs
+  // ---- 3-D (template parameter D3): b = local z plane; third gradient gz = c2r(C) ----
+  const double2* Cf = nullptr;  // [zl][kr][y]   IFFT_y IFFT_z (i*m*s')
+  int nzg = 1, zoff = 0;        // global nz (stride of separable z tables) and this rank's first plane
 };
 
 // ---- pieces of k_fused_x (free functions so that every register-array index is a compile-time constant) ----
@@ -409,6 +482,19 @@ __device__ __forceinline__ void x_lower(double2& ve, int e, int t, double2 Av, d
     sm[pad_idx(NX - k)] = make_double2(Xx + Bv.y, Bv.x - Xy);
   }
 }
+// same packing for two plain half-spectra X = C0 (-> gz of row 0), Y = C1 (-> gz of row 1)
+template <int NX>
+__device__ __forceinline__ void x_lower_plain(double2& ve, int e, int t, double2 Xv, double2 Yv,
+                                              double2* __restrict__ sm) {
+  constexpr int T = Cfg<NX>::T;
+  const int k = t + T * e;
+  if (e == 0 && t == 0) {
+    ve = make_double2(Xv.x, Yv.x);
+  } else {
+    ve = make_double2(Xv.x - Yv.y, Xv.y + Yv.x);
+    sm[pad_idx(NX - k)] = make_double2(Xv.x + Yv.y, Yv.x - Xv.y);
+  }
+}
 // bin k = NX/2: real part only (c2r semantics)
 template <int NX>
 __device__ __forceinline__ void x_nyquist(int t, const double2* Ab, const double2* Bb, int ny, int q,
@@ -421,18 +507,23 @@ __device__ __forceinline__ void x_nyquist(int t, const double2* Ab, const double
   }
 }
 // velocity row -> TMEM (its latency hides behind the inverse transform that follows)
-template <int NX, int VMODE>
+// D3W: the pair (w of row 0, w of row 1) instead of (u, v) of row q
+template <int NX, int VMODE, bool D3W = false, bool D3 = false>
 __device__ __forceinline__ void x_request_uv(const XArgs& a, size_t voff, int q, int t, uint32_t t_uv) {
   constexpr int T = Cfg<NX>::T;
   constexpr int UB = 8;  // velocity request batch
   if (VMODE != 2) {
+    // 3-D: one opaque base per field and compile-time offsets T*e, so that no per-element address outlives this call
+    // (hoisted out of the row loop they would cost 64 registers)
+    const size_t i0 = D3 ? fft::opaque(voff + (size_t)q * NX + t) : 0;
 #pragma unroll
     for (int h = 0; h < 16 / UB; ++h) {
       double2 uv[UB];
 #pragma unroll
       for (int j = 0; j < UB; ++j) {
-        const size_t i = voff + (size_t)q * NX + t + T * (UB * h + j);
+        const size_t i = (D3 ? i0 : voff + (size_t)q * NX + t) + T * (UB * h + j);
         if (a.ablate & 2) uv[j] = make_double2(0.5, 0.25);
+        else if (D3W) uv[j] = make_double2(tmem::ldg64(a.va.arr[2] + i), tmem::ldg64(a.va.arr[2] + i + NX));
         else uv[j] = make_double2(tmem::ldg64(a.va.arr[0] + i), tmem::ldg64(a.va.arr[1] + i));
       }
 #pragma unroll
@@ -442,7 +533,8 @@ __device__ __forceinline__ void x_request_uv(const XArgs& a, size_t voff, int q,
   tmem::wait_st();
 }
 // physical space: v = gx + i*gy at x = t + T*e;  p = -u*gx - v*gy  (TAD.jl:764)
-template <int NX, int VMODE, int Q>
+// D3: both rows' partial products are parked in shared memory (ps[Q*NX + x]); the w*gz term follows in x_product_z
+template <int NX, int VMODE, int Q, bool D3>
 __device__ __forceinline__ void x_product(const XArgs& a, const double2 (&v)[16], double2 (&w)[16],
                                           double* __restrict__ ps, int t, uint32_t t_uv, int b, int pair) {
   constexpr int T = Cfg<NX>::T;
@@ -458,16 +550,44 @@ __device__ __forceinline__ void x_product(const XArgs& a, const double2 (&v)[16]
       const double2 g = v[out_slot<NX>(e)];
       double u, vv;
       if (VMODE == 2) {
-        u = sep_eval(a.va.sep[0], x, row, 0, NX, a.ny, 1, 2);
-        vv = sep_eval(a.va.sep[1], x, row, 0, NX, a.ny, 1, 2);
+        u = sep_eval(a.va.sep[0], x, row, D3 ? a.zoff + b : 0, NX, a.ny, a.nzg, D3 ? 3 : 2);
+        vv = sep_eval(a.va.sep[1], x, row, D3 ? a.zoff + b : 0, NX, a.ny, a.nzg, D3 ? 3 : 2);
       } else {
         u = uv[j].x;
         vv = uv[j].y;
-        if (a.va.ushift) u += a.va.ushift[b * a.ny + row];  // layered flows: u + U(y, layer)  (TAD.jl:795)
+        if (!D3 && a.va.ushift) u += a.va.ushift[b * a.ny + row];  // layered flows: u + U(y, layer)  (TAD.jl:795)
       }
       const double p = -u * g.x - vv * g.y;
-      if (Q == 0) ps[x] = p;                     // row 0: parked in shared memory while row 1 runs
+      if (D3) ps[Q * NX + x] = p;
+      else if (Q == 0) ps[x] = p;                // row 0: parked in shared memory while row 1 runs
       else w[e] = make_double2(ps[x], p);        // row 1: packed with row 0 as p_y + i*p_{y+1} for the forward FFT
+    }
+  }
+}
+// 3-D: v = gz(row 0) + i*gz(row 1);  p_q -= w_q * gz_q  (TAD.jl:781), completed in the shared-memory parking rows
+template <int NX, int VMODE>
+__device__ __forceinline__ void x_product_z(const XArgs& a, const double2 (&v)[16], double* __restrict__ ps, int t,
+                                            uint32_t t_uv, int b, int pair) {
+  constexpr int T = Cfg<NX>::T;
+  constexpr int PB = 4;
+#pragma unroll
+  for (int c = 0; c < 16 / PB; ++c) {
+    double2 ww[PB];
+    if (VMODE != 2) tmem::ldn<PB>(t_uv + 4 * PB * c, ww);
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int e = PB * c + j, x = t + T * e;
+      const double2 g = v[out_slot<NX>(e)];
+      double w0, w1;
+      if (VMODE == 2) {
+        w0 = sep_eval(a.va.sep[2], x, 2 * pair, a.zoff + b, NX, a.ny, a.nzg, 3);
+        w1 = sep_eval(a.va.sep[2], x, 2 * pair + 1, a.zoff + b, NX, a.ny, a.nzg, 3);
+      } else {
+        w0 = ww[j].x;
+        w1 = ww[j].y;
+      }
+      ps[x] = ps[x] - w0 * g.x;
+      ps[NX + x] = ps[NX + x] - w1 * g.y;
     }
   }
 }
@@ -478,7 +598,8 @@ __device__ __forceinline__ void x_product(const XArgs& a, const double2 (&v)[16]
 // so ONE 256-bit load per k fetches both rows of the pair (half the L1 tag look-ups of two 16-byte gathers, one
 // memory round trip instead of two); row 1's share is parked in TMEM until row 0 is done.  The velocity rows are
 // requested before each inverse transform and parked in TMEM as well, so their latency hides behind the FFT.
-template <int NX, int VMODE, int NT>
+// D3 = row kernel of the fused 3-D engine: b = local z plane, a third inverse transform carries gz of both rows.
+template <int NX, int VMODE, int NT, bool D3 = false>
 __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
   constexpr int T = Cfg<NX>::T, F = NT / T, PADN = Cfg<NX>::PADN, H = NX / 2;
   constexpr int TCOLS = NT > 128 ? 256 : 128;
@@ -502,11 +623,19 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
   const int b = blockIdx.y;
   const int ny = a.ny;
   double2* sm = smem + grp * PADN;
-  double* ps = reinterpret_cast<double*>(smem + F * PADN) + grp * NX;  // row-0 product, parked while row 1 runs
+  // row-0 product (3-D: both rows' partial products), parked while the other transforms run
+  double* ps = reinterpret_cast<double*>(smem + F * PADN) + grp * (D3 ? 2 : 1) * NX;
   const double2* Ab = a.A + (size_t)b * a.nkr * ny + 2 * pair;
   const double2* Bb = a.Bf + (size_t)b * a.nkr * ny + 2 * pair;
-  const size_t voff = (size_t)b * a.va.member_stride + (size_t)(2 * pair) * NX;
+  const size_t voff = (D3 ? (size_t)b * ny * NX : (size_t)b * a.va.member_stride) + (size_t)(2 * pair) * NX;
   double2 v[16];
+  if (D3) {   // the third transform's inputs: pulled into L2 now, read after the first two transforms
+    // (strides pass through fft::opaque so that these addresses are recomputed, not kept live across the transforms)
+    const double2* Cb = a.Cf + (size_t)b * a.nkr * ny + 2 * pair + (size_t)t * ny;
+    const size_t se = fft::opaque((size_t)T * ny);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) prefetch_l2(Cb + e * se);
+  }
 
   // row 0's inputs, and the parking of row 1's
 #pragma unroll
@@ -526,9 +655,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
 #pragma unroll
     for (int j = 0; j < GB; ++j) x_lower<NX>(v[GB * h + j], GB * h + j, t, A0[j], B0[j], a.ax.kx, sm);
   }
+  constexpr int NQ = D3 ? 3 : 2;   // 3-D: a third pass of the same loop transforms (gz row 0, gz row 1)
 #pragma unroll 1
-  for (int q = 0; q < 2; ++q) {  // deliberately NOT unrolled: one copy of the inverse transform keeps register
-                                 // pressure (and the instruction footprint) down
+  for (int q = 0; q < NQ; ++q) {  // deliberately NOT unrolled: one copy of the inverse transform keeps register
+                                  // pressure (and the instruction footprint) down
     if (q == 1) {
       __syncthreads();           // exchange buffer free (row 0's transform readers are done)
 #pragma unroll
@@ -538,17 +668,65 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
         x_lower<NX>(v[2 * h], 2 * h, t, AB[0], AB[1], a.ax.kx, sm);
         x_lower<NX>(v[2 * h + 1], 2 * h + 1, t, AB[2], AB[3], a.ax.kx, sm);
       }
+      if constexpr (D3) {        // the parking slot is free again: fetch the (C row 0, C row 1) pairs into it
+        const double2* Cb = a.Cf + (size_t)b * a.nkr * ny + 2 * pair + (size_t)t * ny;
+        const size_t se = fft::opaque((size_t)T * ny);
+#pragma unroll
+        for (int h = 0; h < 8 / GB; ++h) {
+          double2 C0[GB], C1[GB];
+#pragma unroll
+          for (int j = 0; j < GB; ++j) tmem::ldg256(Cb + (GB * h + j) * se, C0[j], C1[j]);
+#pragma unroll
+          for (int j = 0; j < GB; ++j) {
+            tmem::st1(t_in + 8 * (GB * h + j), C0[j]);
+            tmem::st1(t_in + 8 * (GB * h + j) + 4, C1[j]);
+          }
+        }
+      }
     }
-    x_nyquist<NX>(t, Ab, Bb, ny, q, a.ax.kx, sm);
-    x_request_uv<NX, VMODE>(a, voff, q, t, t_uv);  // includes tcgen05.wait::st for the parked inputs as well
+    if constexpr (D3) {
+      if (q == 2) {
+        __syncthreads();         // exchange buffer free (row 1's transform readers are done)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          double2 CC[4];         // (C0, C1) of k-slots 2h, 2h+1
+          tmem::ldn<4>(t_in + 16 * h, CC);
+          x_lower_plain<NX>(v[2 * h], 2 * h, t, CC[0], CC[1], sm);
+          x_lower_plain<NX>(v[2 * h + 1], 2 * h + 1, t, CC[2], CC[3], sm);
+        }
+        if (t == 0) {
+          double2 C0, C1;
+          tmem::ldg256(a.Cf + (size_t)b * a.nkr * ny + 2 * pair + (size_t)H * ny, C0, C1);
+          sm[pad_idx(H)] = make_double2(C0.x, C1.x);
+        }
+        x_request_uv<NX, VMODE, true, true>(a, voff, 0, t, t_uv);
+      } else {
+        x_nyquist<NX>(t, Ab, Bb, ny, q, a.ax.kx, sm);
+        x_request_uv<NX, VMODE, false, true>(a, voff, q, t, t_uv);
+      }
+    } else {
+      x_nyquist<NX>(t, Ab, Bb, ny, q, a.ax.kx, sm);
+      x_request_uv<NX, VMODE>(a, voff, q, t, t_uv);  // includes tcgen05.wait::st for the parked inputs as well
+    }
     __syncthreads();
 #pragma unroll
     for (int e = 8; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
     fft::fft_cta<NX, +1>(v, sm, t, a.tw);
-    if (q == 0) x_product<NX, VMODE, 0>(a, v, v, ps, t, t_uv, b, pair);
+    if constexpr (D3) {
+      if (q == 0) x_product<NX, VMODE, 0, true>(a, v, v, ps, t, t_uv, b, pair);
+      else if (q == 1) x_product<NX, VMODE, 1, true>(a, v, v, ps, t, t_uv, b, pair);
+      else x_product_z<NX, VMODE>(a, v, ps, t, t_uv, b, pair);
+    } else {
+      if (q == 0) x_product<NX, VMODE, 0, false>(a, v, v, ps, t, t_uv, b, pair);
+    }
   }
   double2 w[16];
-  x_product<NX, VMODE, 1>(a, v, w, ps, t, t_uv, b, pair);
+  if constexpr (D3) {            // both rows' finished products come back from shared memory (same thread wrote them)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) w[e] = make_double2(ps[t + T * e], ps[NX + t + T * e]);
+  } else {
+    x_product<NX, VMODE, 1, false>(a, v, w, ps, t, t_uv, b, pair);
+  }
 
   // ---------------- forward transform of the row pair packed as p_y + i*p_{y+1} ----------------
   fft::fft_cta<NX, -1>(w, sm, t, a.tw);
@@ -745,7 +923,9 @@ __global__ void __launch_bounds__(256, 2) k_fft_pair_test(const double2* __restr
   tmem::free_cta<256>(tbase);
 }
 
-bool is_fused_size(int64_t n) { return n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096; }
+bool is_fused_size(int64_t n) {
+  return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096;
+}
 
 // twiddle tables of one length, forward sign, rounded from long double
 struct TwiddleSet {
@@ -754,9 +934,10 @@ struct TwiddleSet {
   void build(int N, int64_t* tally) {
     std::vector<double2> h2(4 * 16), h3(4 * 256);
     const long double PI2 = 6.283185307179586476925286766559005768L;
+    const int n2 = N < 256 ? N : 256;  // two-pass lengths (64, 128) keep their last-pass twiddles w_N^(2^m k) here
     for (int m = 0; m < 4; ++m)
       for (int k = 0; k < 16; ++k) {
-        long double ang = -PI2 * (long double)((k << m) % 256) / 256.0L;
+        long double ang = -PI2 * (long double)((k << m) % n2) / (long double)n2;
         h2[m * 16 + k] = make_double2((double)cosl(ang), (double)sinl(ang));
       }
     for (int m = 0; m < 4; ++m)

@@ -433,6 +433,9 @@ int32_t ptf_create(const ptf_desc* d, ptf_handle** out) {
       if (one_d) {
         if (!fused1d_engine_supports(h->ctx, &why)) throw Error(PTF_EUNSUPPORTED, "fused engine: " + why);
         h->engine = make_fused1d_engine(h->ctx);
+      } else if (h->ctx.g.ndim == 3) {
+        if (!fused3d_engine_supports(h->ctx, &why)) throw Error(PTF_EUNSUPPORTED, "fused engine: " + why);
+        h->engine = make_fused3d_engine(h->ctx);
       } else {
         if (!fused_engine_supports(h->ctx, &why)) throw Error(PTF_EUNSUPPORTED, "fused engine: " + why);
         h->engine = make_fused_engine(h->ctx);
@@ -441,6 +444,8 @@ int32_t ptf_create(const ptf_desc* d, ptf_handle** out) {
       h->engine = make_fused1d_engine(h->ctx);
     } else if (want == PTF_ENGINE_AUTO && !h->ctx.g.slab && fused_engine_supports(h->ctx, &why)) {
       h->engine = make_fused_engine(h->ctx);
+    } else if (want == PTF_ENGINE_AUTO && fused3d_engine_supports(h->ctx, &why)) {
+      h->engine = make_fused3d_engine(h->ctx);
     } else {
       h->engine = make_cufft_engine(h->ctx);
     }

@@ -178,6 +178,8 @@ struct Context {
 std::unique_ptr<Engine> make_cufft_engine(Context& ctx);
 std::unique_ptr<Engine> make_fused_engine(Context& ctx);  // throws PTF_EUNSUPPORTED when the grid does not qualify
 bool fused_engine_supports(const Context& ctx, std::string* why);
+std::unique_ptr<Engine> make_fused3d_engine(Context& ctx);  // fused 3-D engine (also slab-decomposed)
+bool fused3d_engine_supports(const Context& ctx, std::string* why);
 void selftest_fft(int n, int dir, int count, const double* in_host, double* out_host);
 std::unique_ptr<Engine> make_slab2d_engine(Context& ctx);
 std::unique_ptr<Engine> make_fused1d_engine(Context& ctx);

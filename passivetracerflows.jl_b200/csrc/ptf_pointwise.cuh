@@ -83,7 +83,9 @@ enum CombineMode : int {
   CM_LSRK = 9,
   // AB3
   CM_AB3_EULER = 10,  // start-up: s0 += dt*k ; rotate history
-  CM_AB3 = 11         // s0 += dt*(23/12 k - 16/12 k1 + 5/12 k2)
+  CM_AB3 = 11,        // s0 += dt*(23/12 k - 16/12 k1 + 5/12 k2)
+  // not a stepper: s0 = Nh (set_c! through the fused 3-D engine's own forward transforms)
+  CM_STORE = 12
 };
 
 struct CombineArgs {
@@ -210,6 +212,10 @@ __device__ __forceinline__ double2 combine_at(const CombinePtrs& P, const Combin
       P.n1[i] = k1;
       P.acc[i] = k;
     } break;
+    case CM_STORE: if (MASK & CMASK_OTHER) {
+      next = Nh;
+      P.s0[i] = Nh;
+    } break;
   }
   return next;
 }
@@ -225,7 +231,8 @@ inline int next_state_slot(int mode) {  // 0 = s0, 1 = s1, 2 = s2
 
 // ---------------------------------------------------------------------------------------------------
 // ETDRK4 coefficients (FF getetdcoeffs / getexpLs): 32-point contour mean around dt*L, evaluated on device.
-// tlayout = 0: arrays indexed [kz][ky][kx] (canonical); 1: [kx][ky] (the fused 2-D engine's transposed layout).
+// tlayout = 0: arrays indexed [kz][ky][kx] (canonical); 1: [kx][ky] (the fused 2-D engine's transposed layout);
+// 2: [kx][ky_local][kz] (the fused 3-D engine's state layout; ny = local rows, yoff = global index of the first).
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double2 cx_mul(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -242,11 +249,16 @@ __device__ __forceinline__ double2 cx_exp(double2 z) {
 
 static __global__ void __launch_bounds__(256) k_etd_coeffs(double* E, double* E2, double* zeta, double* alpha,
                                                            double* beta, double* gamma, AxisTables ax, int64_t nkr,
-                                                           int64_t ny, int64_t nz, double dt, int tlayout) {
+                                                           int64_t ny, int64_t nz, double dt, int tlayout,
+                                                           int64_t yoff = 0) {
   int64_t n = nkr * ny * nz;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t ix, iy, iz;
-    if (tlayout) {
+    if (tlayout == 2) {
+      iz = i % nz;
+      iy = yoff + (i / nz) % ny;
+      ix = i / (nz * ny);
+    } else if (tlayout) {
       iy = i % ny;
       ix = i / ny;
       iz = 0;

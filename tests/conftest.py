@@ -14,9 +14,14 @@ def pytest_configure(config):
 
 
 def has_gpu():
-    # A broken torch import must fail the run loudly, never turn every GPU test into a silent skip.
-    import torch
-    return torch.cuda.is_available()
+    # Ask the product library itself (ptf_device_count): the CPU-only suite then does not need torch at all, and a
+    # missing / broken libptf_b200.so fails the run loudly instead of turning every GPU test into a silent skip.
+    import ctypes
+
+    import ptf_b200
+    n = ctypes.c_int32(0)
+    ptf_b200._capi.load().ptf_device_count(ctypes.byref(n))
+    return n.value > 0
 
 
 def pytest_collection_modifyitems(config, items):

@@ -16,7 +16,7 @@ def _P():
     return ptf_b200
 
 
-@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096])
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096])
 @pytest.mark.parametrize("direction", [-1, 1])
 def test_fft_core_matches_numpy(n, direction):
     P = _P()

@@ -178,6 +178,42 @@ def test_coupled_tracer_matches_oracle(engine, n):
     g.close()
 
 
+def test_two_tracers_coupled_to_one_flow_are_ordered_across_streams():
+    """The flow adopts the stream of the tracer that coupled last; stepping the OTHER tracer through step_coupled runs
+    its kernels on a different stream than the flow's and must be ordered with events (data race)."""
+    n, kappa, dt = 128, 0.002, 2.5e-3
+    o, g = _pair(n=n, stepper="FilteredRK4", dt=dt, amp=0.5)
+    ad1 = P().Problem(g, kappa=kappa, stepper="FilteredRK4")
+    ad2 = P().Problem(g, kappa=2 * kappa, stepper="FilteredRK4")     # couples second: the flow now runs on ad2's stream
+    o.updatevars()
+    ots = [OracleProblem(n=(n, n), L=(2 * np.pi,) * 2, kappa=(k, k), dt=dt, stepper="FilteredRK4", velocity="layered",
+                         steady=True, nbatch=2) for k in (kappa, 2 * kappa)]
+    c0 = _tracer_c0(n)
+    for ot, ad in zip(ots, (ad1, ad2)):
+        ot.set_c(c0)
+        ad.set_c(c0)
+    nsteps = 10
+    for i in range(nsteps):
+        for ot in ots:
+            ot.set_layered_velocity(o.u, o.v, o.params.U)
+            ot.stepforward(1)
+        o.stepforward(1)
+        o.updatevars()
+    for i in range(nsteps // 2):                     # the users' loop with two tracers: tracer 2 alone, then
+        ad2.stepforward(1)                           # tracer 1 + flow + updatevars! inside the library (cross-stream)
+        P().MultiLayerQG.step_coupled(ad1, 1)
+    for i in range(nsteps // 2):
+        ad1.stepforward(1)
+        P().MultiLayerQG.step_coupled(ad2, 1)        # same-stream path
+    assert ad1.clock.step == nsteps and ad2.clock.step == nsteps and g.clock.step == o.step
+    assert rel_l2(ots[0].updatevars(), ad1.updatevars()) < TOL_20
+    assert rel_l2(ots[1].updatevars(), ad2.updatevars()) < TOL_20
+    assert rel_l2(o.sol, g.sol) < TOL_20
+    ad1.close()
+    ad2.close()
+    g.close()
+
+
 def test_reference_kat_diffusion_multilayerqg_with_device_flow():
     """test/test_traceradvectiondiffusion.jl:302-355 with the flow solver on the device (zero flow, release after 50
     flow steps, both layers must match the analytic diffusion solution to nx·ny·nsteps·1e-12)."""
