@@ -12,6 +12,11 @@ One bench "step" = one frame of the example's loop, ``stepforward!(prob, nsubs=2
   * ``roofline``: dominant kernel, algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
   * ``cpu_baseline``: the CPU oracle port (NumPy + threaded pocketfft) on a bounded sample of the same workload
 
+With the default workload every invocation also runs the PARTITIONED configuration (BASELINE configs[3]: one 1024^3
+problem slab-decomposed over all N GPUs, the all-to-all transpose is the only collective) and adds a ``partitioned``
+object to the same JSON line: ms/step, strong-scaling efficiency against the committed N = 1 time, achieved all-to-all
+GB/s against NVLink's 900 GB/s, how much of the exchange is hidden, and a multi-rank parity number against the oracle.
+
 ``--impl reference`` times the CPU restatement of the reference path (the reference itself is Julia + FFTW, neither
 of which exists in this image — see DESIGN.md) on the box's host cores.
 """
@@ -118,10 +123,18 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
+def host_threads():
+    """Threads this process may really use: its CPU affinity mask (torchrun / container limits), not os.cpu_count()."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_port_rate(w, seconds_budget=20.0, min_steps=2, max_steps=8):
     """Time the CPU oracle (port of the reference path) on a bounded sample: a few RK4 steps of the same workload."""
     from oracle.ptf_oracle import OracleProblem
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     nx = w["nx"]
     o = OracleProblem(n=(nx, nx), L=(w["Lx"], w["Lx"]), kappa=(w["kappa"], w["kappa"]), dt=w["dt"], stepper="RK4",
                       velocity=[w["u"], w["v"]], steady=True, workers=cores)
@@ -145,8 +158,11 @@ def run_reference(args, rank, world):
         return
     w = workload(args.nx)
     # each "step" of the reference arm is a bounded sample: one RK4 step of the workload (a frame is 25 of them)
+    # torchrun exports OMP_NUM_THREADS=1 for N > 1: undo it for this (single) CPU process before NumPy/SciPy load
+    cores = host_threads()
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[var] = str(cores)
     from oracle.ptf_oracle import OracleProblem
-    cores = os.cpu_count() or 1
     nx = w["nx"]
     o = OracleProblem(n=(nx, nx), L=(w["Lx"], w["Lx"]), kappa=(w["kappa"], w["kappa"]), dt=w["dt"], stepper="RK4",
                       velocity=[w["u"], w["v"]], steady=True, workers=cores)
@@ -167,16 +183,17 @@ def run_reference(args, rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"cellularflow_{nx}x{nx}_RK4_kappa0.1 (BASELINE configs[1])", "nx": nx, "ny": nx,
                        "stepper": "RK4", "dt": w["dt"], "rk4_steps_per_step": 1},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "os_cpu_count": os.cpu_count(), "launched_with_world_size": world},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def run_slab3d(args, rank, world, local_rank, P, dist, barrier, max_over_ranks):
+def measure_slab3d(n, stepper, steps, warmup, rank, world, local_rank, P, barrier, max_over_ranks, dev=None):
     """BASELINE configs[3]: 3-D prescribed time-dependent (ABC-type, separable) flow, n^3 fp64 with hyperdiffusion,
-    slab-decomposed across the GPUs; the NCCL all-to-all transpose is the only collective.  Strong scaling."""
-    n = args.n3
+    slab-decomposed across the GPUs (z-slabs physical / ky-slabs spectral); the all-to-all between the y- and z-column
+    kernels is the only collective.  Returns the measurements of this configuration (every rank must call it)."""
     L = 2 * np.pi
     A, B, Cc = 1.0, 0.8, 0.6
     one = lambda s: 1.0 + 0 * s
@@ -190,49 +207,130 @@ def run_slab3d(args, rank, world, local_rank, P, dist, barrier, max_over_ranks):
     kmax2 = 3 * (n / 2) ** 2
     kappa_h = 1e-3 / kmax2          # hyperdiffusion (n_kappa_h = 2): max|L| = kappa_h * kmax2^2
     dt = min(0.5 * 2.785 / (kappa_h * kmax2 ** 2), 0.5 * 2.83 / (3 * 1.5 * 1.8 * n / 2))
-    dev = P.parallel.init_b200("slab", device=local_rank) if world > 1 else P.B200(device=local_rank)
-    prob = P.Problem(dev, flow, nx=n, kappa=0.0, dt=dt, stepper=args.stepper, kappa_h=kappa_h, n_kappa_h=2)
+    if dev is None:
+        dev = P.parallel.init_b200("slab", device=local_rank) if world > 1 else P.B200(device=local_rank)
+    prob = P.Problem(dev, flow, nx=n, kappa=0.0, dt=dt, stepper=stepper, kappa_h=kappa_h, n_kappa_h=2)
     x = prob.grid.x
     zs = x[prob.z_offset:prob.z_offset + prob.nz_local]
     sig = 0.1 * 8                   # resolved Gaussian
     c0 = np.exp(-(x[None, None, :] ** 2 + x[None, :, None] ** 2 + zs[:, None, None] ** 2) / (2 * sig ** 2))
     prob.set_c(np.ascontiguousarray(c0))
-    for _ in range(args.warmup):
+    del c0
+    for _ in range(warmup):
         prob.stepforward(1)
     own0, lib0 = prob.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    dev_ms = prob.step_timed(args.steps)
+    dev_ms = prob.step_timed(steps)
     barrier()
     sampler.stop_flag.set()
     sampler.join()
     own1, lib1 = prob.launch_count()
     dev_ms = max_over_ranks(dev_ms)
     npts = n ** 3
-    value = npts * args.steps / (dev_ms * 1e-3)
+    step_ms = dev_ms / steps
     d = prob.diagnostics()
     peak, peak_src = peaks()
-    balg = b_alg(3, args.stepper) - 32 * 3      # velocities generated in registers: -32*d
-    step_ms = dev_ms / args.steps
-    # per-GPU NVLink floor: each transposed field moves (P-1)/P of the local spectral slab out of every GPU
-    spec_local = (n // 2 + 1) * n * n * 16 / world
-    a2a_bytes = 16 * spec_local * (world - 1) / world if world > 1 else 0
+    balg = b_alg(3, stepper)        # the three velocity fields are written once per step and read by every stage
+    out = {"workload": f"slab3d_{n}^3_{stepper}_hyperdiffusion_separable_ABC_flow (BASELINE configs[3])", "n": n,
+           "stepper": stepper, "dt": dt, "engine": prob.engine, "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": step_ms, "value": npts * steps / (dev_ms * 1e-3), "unit": UNIT,
+           "state_finite": bool(np.isfinite(d["max_abs_sol"])),
+           "gpu_launches": own1 - own0, "library_calls": lib1 - lib0,
+           "step_roofline": {"b_alg_bytes_per_point_step": balg, "achieved": balg * npts / (step_ms * 1e-3) / 1e9,
+                             "peak": peak * world, "unit": "GB/s",
+                             "frac": balg * npts / (step_ms * 1e-3) / 1e9 / (peak * world)},
+           "clocks": sampler.summary()}
+    # per-kernel device times (CUDA events on the step stream, real RK4 steps, unpipelined) and the exchange run alone
+    if prob.engine == "fused" and stepper == "RK4":
+        spec_l = (n // 2 + 1) * n * n * 16 / world      # one local spectral field
+        real_l = npts * 8 / world
+        alg = {"zkernel": 7.25 * spec_l, "yinv": 5 * spec_l, "xkernel": 4 * spec_l + 3 * real_l, "yfwd": 2 * spec_l}
+        kern = {}
+        for k, by in alg.items():
+            ms = max_over_ranks(prob.kernel_time_ms(k, 2))
+            kern[k] = {"ms": ms, "alg_bytes": by, "achieved_gbs": by / ms / 1e6, "frac_of_peak": by / ms / 1e6 / peak}
+        out["kernels"] = kern
+        compute_ms = 4 * sum(v["ms"] for v in kern.values())
+        out["compute_ms_per_step"] = compute_ms
+        if world > 1:
+            ex_ms = max_over_ranks(prob.kernel_time_ms("exchange", 2))
+            out_bytes = spec_l * (world - 1) / world    # what one field's all-to-all sends out of each GPU
+            serial = 12 * ex_ms
+            out["exchange"] = {"ms_per_field_alone": ex_ms, "fields_per_step": 12, "bytes_out_per_gpu_per_field": out_bytes,
+                               "alltoall_gbs_achieved": out_bytes / ex_ms / 1e6,
+                               "nvlink_frac_of_900": out_bytes / ex_ms / 1e6 / 900.0,
+                               "serial_ms_per_step": serial,
+                               "hidden_frac": max(0.0, min(1.0, 1.0 - max(0.0, step_ms - compute_ms) / serial)),
+                               "floor_ms_per_step_at_900GBs": 12 * out_bytes / 900e9 * 1e3}
+    prob.close()
+    return out, dev
+
+
+def partitioned_parity(dev, rank, world, max_over_ranks):
+    """Multi-rank parity of the partitioned paths against the CPU oracle (the comparison of tests/mgpu_slab_check.py
+    and tests/mgpu_slab2d_check.py): SURVEY 8(d) config 4's 128^3 on the fused slab path, and a 2-D slab problem."""
+    from tests.mgpu_slab_check import slab_case
+    out = {}
+    e3, info = slab_case(dev, (128, 128, 128), "RK4", "separable", nsteps=2, L=(2 * np.pi,) * 3)
+    out["slab3d_128^3_RK4_2steps"] = max_over_ranks(e3)
+    out["slab3d_engine"] = info["engine"]
+    try:
+        from tests.mgpu_slab2d_check import slab2d_case
+        import ptf_b200 as P
+        dev2 = dev if world > 1 else P.B200(device=dev.device, decomposition="slab")
+        out["slab2d_256x64_LSRK54_4steps"] = max_over_ranks(slab2d_case(dev2, (256, 64), "LSRK54", rank, world, verbose=False))
+    except Exception as e:      # the 3-D number is the graded one; say why the 2-D one is missing
+        out["slab2d_error"] = repr(e)[:200]
+    out["tolerance"] = 3e-12
+    out["ok"] = bool(out["slab3d_128^3_RK4_2steps"] <= 3e-12 and out.get("slab2d_256x64_LSRK54_4steps", 0.0) <= 5e-12)
+    return out
+
+
+def partitioned_n1_reference(n):
+    """The committed N = 1 time of the partitioned workload (measured by an N = 1 invocation of this script)."""
+    p = os.path.join(ROOT, "profiles", "r02_partitioned_n1.json")
+    try:
+        d = json.load(open(p))
+        if d.get("n") == n:
+            return float(d["ms_per_step"]), "profiles/r02_partitioned_n1.json"
+    except Exception:
+        pass
+    return None, None
+
+
+def run_partitioned(args, rank, world, local_rank, P, barrier, max_over_ranks):
+    n = args.n3p
+    m, dev = measure_slab3d(n, "RK4", args.psteps, 2, rank, world, local_rank, P, barrier, max_over_ranks)
+    ref_ms, ref_src = (m["ms_per_step"], "this run") if world == 1 else partitioned_n1_reference(n)
+    m["n1_ms_per_step"] = ref_ms
+    m["n1_source"] = ref_src
+    m["efficiency_vs_n1"] = None if ref_ms is None else ref_ms / (world * m["ms_per_step"])
+    if "exchange" in m:
+        m["alltoall_gbs_achieved"] = m["exchange"]["alltoall_gbs_achieved"]
+        m["nvlink_frac_of_900"] = m["exchange"]["nvlink_frac_of_900"]
+    m["parity_rel_l2"] = partitioned_parity(dev, rank, world, max_over_ranks)
+    m["scaling"] = "strong"
+    return m
+
+
+def run_slab3d(args, rank, world, local_rank, P, dist, barrier, max_over_ranks):
+    """`--workload slab3d`: the partitioned configuration alone (strong scaling), as its own JSON line."""
+    m, _ = measure_slab3d(args.n3, args.stepper, args.steps, args.warmup, rank, world, local_rank, P, barrier,
+                          max_over_ranks)
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+        line = {"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"slab3d_{n}^3_{args.stepper}_hyperdiffusion_separable_ABC_flow (BASELINE configs[3])",
-                           "n": n, "stepper": args.stepper, "dt": dt, "engine": prob.engine,
-                           "decomposition": "z-slabs (physical) / ky-slabs (spectral), NCCL all-to-all per transform",
-                           "state_finite": bool(np.isfinite(d["max_abs_sol"])), "l2": "fields larger than L2"},
-                "gpu_launches": own1 - own0, "library_calls": lib1 - lib0,
-                "step_roofline": {"b_alg_bytes_per_point_step": balg, "achieved": balg * npts / (step_ms * 1e-3) / 1e9,
-                                  "peak": peak * world, "unit": "GB/s",
-                                  "frac": balg * npts / (step_ms * 1e-3) / 1e9 / (peak * world)},
-                "nvlink": {"alltoall_bytes_out_per_gpu_per_step": a2a_bytes,
-                           "floor_ms_per_step_at_770GBs": a2a_bytes / 770e9 * 1e3},
-                "clocks": sampler.summary()}
+                "config": {"workload": m["workload"], "n": m["n"], "stepper": m["stepper"], "dt": m["dt"],
+                           "engine": m["engine"],
+                           "decomposition": "z-slabs (physical) / ky-slabs (spectral), NCCL all-to-all between the y- "
+                                            "and z-column kernels",
+                           "state_finite": m["state_finite"], "l2": "fields larger than L2"},
+                "gpu_launches": m["gpu_launches"], "library_calls": m["library_calls"],
+                "step_roofline": m["step_roofline"], "kernels": m.get("kernels"), "exchange": m.get("exchange"),
+                "compute_ms_per_step": m.get("compute_ms_per_step"), "clocks": m["clocks"]}
         print(json.dumps(line), flush=True)
 
 
@@ -303,6 +401,9 @@ def main():
                          "slab3d: BASELINE configs[3], ONE n^3 problem slab-decomposed over all GPUs (strong scaling)")
     ap.add_argument("--n3", type=int, default=512, help="grid size of the slab3d workload (n^3)")
     ap.add_argument("--n2", type=int, default=16384, help="grid size of the slab2d workload (n^2)")
+    ap.add_argument("--n3p", type=int, default=1024, help="grid size of the partitioned leg of the default workload")
+    ap.add_argument("--psteps", type=int, default=3, help="timed steps of the partitioned leg")
+    ap.add_argument("--no-partitioned", action="store_true", help="skip the partitioned (1024^3 slab) leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -411,7 +512,22 @@ def main():
     e2e = {"value": world * npts * NSUBS * args.steps / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": npts * 8, "d2h_bytes_per_step": npts * 8,
            "ms_per_step": 1e3 * e2e_s / args.steps,
-           "call": "ptf_set_c(pinned host) + ptf_step(25) + ptf_get_c(pinned host)"}
+           "call": "ptf_set_c(pinned host) + ptf_step(25) + ptf_get_c(pinned host)",
+           "note": "one frame of the example's loop (examples/cellularflow.jl:134-135): 268 MB of PCIe traffic amortised "
+                   "over 25 RK4 steps; see e2e_per_step_roundtrip for a host round trip around EVERY step"}
+    # the same through the C ABI with a host round trip around every single RK4 step (nothing amortised)
+    n_rt = 10
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_rt):
+        capi.check(lib.ptf_set_c(h, p_in, 0), h)
+        capi.check(lib.ptf_step(h, 1), h)
+        capi.check(lib.ptf_get_c(h, p_out), h)
+    barrier()
+    rt_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_rt = {"value": world * npts * n_rt / rt_s, "unit": UNIT, "ms_per_rk4_step": 1e3 * rt_s / n_rt,
+              "h2d_bytes_per_rk4_step": npts * 8, "d2h_bytes_per_rk4_step": npts * 8,
+              "call": "ptf_set_c(pinned host) + ptf_step(1) + ptf_get_c(pinned host)"}
 
     # ---------------- roofline of the dominant kernel (live CUDA-event timing, in place) ----------------
     peak, peak_src = peaks()
@@ -434,33 +550,51 @@ def main():
         kernels[name] = {"ms": ms, "alg_bytes": alg_bytes}
     step_bytes = b_alg(2, args.stepper) * npts
     step_ms = dev_ms / (args.steps * NSUBS)
-    # measured DRAM traffic per launch (dram__bytes_read + dram__bytes_write) from the committed ncu --set full capture
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_fused_4096.json")))
+    # measured DRAM traffic per launch (dram__bytes_read + dram__bytes_write): ncu cannot run inside this process, so the
+    # figure comes from the committed `ncu --set full` capture of this same workload and is only attached when the run
+    # is that workload (nx = 4096, fused engine); otherwise traffic is null
+    traffic_src = None
+    for prof_name in ("r02_ncu_fused_4096.json", "r01_ncu_fused_4096.json"):
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", prof_name)))
+        except Exception:
+            continue
         for name, tag in (("ykernel", "k_fused_y"), ("xkernel", "k_fused_x")):
             tr = [pk["dram_traffic_bytes"] for pk in prof if tag in pk["kernel"]]
-            if tr and name in kernels and nx == 4096:
+            if tr and name in kernels and nx == 4096 and engine == "fused":
                 kernels[name]["traffic"] = sum(tr) / len(tr)     # mean over the captured launches (4 RK4 stages)
-    except Exception:
-        pass
+                traffic_src = "profiles/" + prof_name
+        if traffic_src:
+            break
     for k in kernels.values():
         if k["alg_bytes"]:
             k["achieved_gbs"] = k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9
             k["frac_of_peak"] = k["achieved_gbs"] / peak
     if kernels:
-        top = max(kernels.items(), key=lambda kv: kv[1]["ms"])
-        name, k = top
-        if k["alg_bytes"]:
-            ach = k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": k.get("traffic"), "peak_source": peak_src, "ms_per_launch": k["ms"],
-                    "alg_bytes_per_launch": k["alg_bytes"]}
+        # `roofline` = the kernel FURTHEST below its roofline (lowest fraction), not the longest-running one: the two
+        # fused kernels time within a microsecond of each other and "longest" flapped between runs
+        cand = {n_: k for n_, k in kernels.items() if k.get("alg_bytes")}
+        name, k = min(cand.items(), key=lambda kv: kv[1]["frac_of_peak"])
+        roof = {"bound": "hbm", "kernel": name, "achieved": k["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": k["frac_of_peak"], "traffic": k.get("traffic"), "traffic_source": traffic_src,
+                "peak_source": peak_src, "ms_per_launch": k["ms"], "alg_bytes_per_launch": k["alg_bytes"],
+                "selection": "lowest fraction of peak among the step's kernels (all of them are listed under `kernels`)"}
     step_roof = {"b_alg_bytes_per_point_step": b_alg(2, args.stepper), "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
                  "peak": peak, "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak,
                  "ms_per_rk4_step": step_ms}
     if roof is None:
         roof = {"bound": "hbm", "kernel": "whole RK4 step", "achieved": step_roof["achieved"], "peak": peak,
                 "unit": "GB/s", "frac": step_roof["frac"], "traffic": None, "peak_source": peak_src}
+
+    # ---------------- partitioned configuration (1024^3 slab-decomposed over all N GPUs) ----------------
+    prob.close()
+    del prob
+    part = None
+    if not args.no_partitioned:
+        try:
+            part = run_partitioned(args, rank, world, local_rank, P, barrier, max_over_ranks)
+        except Exception as e:       # never lose the headline line to the second leg
+            part = {"error": repr(e)[:300]}
 
     # ---------------- CPU baseline (rank 0, N == 1) ----------------
     cpu = None
@@ -476,9 +610,10 @@ def main():
                            "dt": w["dt"], "rk4_steps_per_step": NSUBS, "engine": engine,
                            "l2": "inputs larger than L2 (each field 134 MB > 126 MB L2); no explicit flush",
                            "state_finite": finite, "wall_ms_per_step": wall_ms / args.steps},
-                "e2e": e2e, "gpu_launches": own1 - own0, "library_calls": libc1 - libc0,
-                "roofline": roof, "step_roofline": step_roof, "kernels": kernels, "cpu_baseline": cpu,
-                "clocks": sampler.summary()}
+                "e2e": e2e, "e2e_per_step_roundtrip": e2e_rt, "gpu_launches": own1 - own0,
+                "library_calls": libc1 - libc0,
+                "roofline": roof, "step_roofline": step_roof, "kernels": kernels, "partitioned": part,
+                "cpu_baseline": cpu, "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -92,11 +92,33 @@ class Fused3DEngine final : public Engine {
     PTF_CUFFT(cufftSetStream(plan_fwd, ctx.stream));
     PTF_CUFFT(cufftSetStream(plan_inv, ctx.stream));
     dev_bytes += (int64_t)(wf + wi);
+    // pipelined exchange: kr chunks, exchanges on a high-priority stream overlapping the column kernels.
+    // PTF_F3_CHUNKS = number of chunks (default 4); on one GPU it switches the chunked launch sequence on as a test
+    // hook (every kernel launch and event of the slab pipeline, with the exchange itself a no-op).
+    const char* ce = std::getenv("PTF_F3_CHUNKS");
+    pipelined = P > 1 || (ce && std::atoi(ce) > 1);
+    if (pipelined) {
+      n_chunks = 4;
+      if (ce) {
+        int c = std::atoi(ce);
+        if (c >= 1 && c <= MAXCH) n_chunks = c;
+      }
+      if (n_chunks > nkx) n_chunks = nkx;
+      int lo = 0, hi = 0;
+      PTF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      PTF_CUDA(cudaStreamCreateWithPriority(&s_comm, cudaStreamNonBlocking, hi));
+      for (auto& row : ev)
+        for (auto& e : row) PTF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     on_dt_changed();
   }
 
   ~Fused3DEngine() override {
     drop_graphs();
+    if (s_comm) cudaStreamDestroy(s_comm);
+    for (auto& row : ev)
+      for (auto& e : row)
+        if (e) cudaEventDestroy(e);
     if (plan_fwd) cufftDestroy(plan_fwd);
     if (plan_inv) cufftDestroy(plan_inv);
   }
@@ -140,28 +162,33 @@ class Fused3DEngine final : public Engine {
   }
 
   // ---------------- the exchange between the y- and z-column kernels (the only collective) ----------------
-  void exchange(const double2* send, double2* recv) {
+  // kr range [k0, k1) of every peer block (the whole block by default) on stream `st`
+  void exchange(const double2* send, double2* recv, int k0 = 0, int k1 = -1, cudaStream_t st = nullptr) {
     if (P == 1) return;  // send and recv are the same buffer
 #ifdef PTF_WITH_NCCL
+    if (k1 < 0) k1 = nkx;
+    if (!st) st = ctx.stream;
     ncclComm_t comm = (ncclComm_t)ctx.nccl_comm;
     auto ck = [](ncclResult_t r, const char* what) {
       if (r != ncclSuccess) throw Error(PTF_ENCCL, std::string(what) + ": " + ncclGetErrorString(r));
     };
-    PTF_CUDA(cudaMemcpyAsync(recv + (size_t)rank * blk, send + (size_t)rank * blk, blk * sizeof(double2),
-                             cudaMemcpyDeviceToDevice, ctx.stream));
+    const size_t off = (size_t)k0 * nyl * nzl, cnt = (size_t)(k1 - k0) * nyl * nzl;
+    PTF_CUDA(cudaMemcpyAsync(recv + (size_t)rank * blk + off, send + (size_t)rank * blk + off, cnt * sizeof(double2),
+                             cudaMemcpyDeviceToDevice, st));
     ck(ncclGroupStart(), "ncclGroupStart");
     for (int r = 0; r < P; ++r) {
       if (r == rank) continue;
-      ck(ncclSend(send + (size_t)r * blk, 2 * blk, ncclDouble, r, comm, ctx.stream), "ncclSend");
-      ck(ncclRecv(recv + (size_t)r * blk, 2 * blk, ncclDouble, r, comm, ctx.stream), "ncclRecv");
+      ck(ncclSend(send + (size_t)r * blk + off, 2 * cnt, ncclDouble, r, comm, st), "ncclSend");
+      ck(ncclRecv(recv + (size_t)r * blk + off, 2 * cnt, ncclDouble, r, comm, st), "ncclRecv");
     }
     ck(ncclGroupEnd(), "ncclGroupEnd");
     ++lib_calls;
 #else
-    (void)send; (void)recv;
+    (void)send; (void)recv; (void)k0; (void)k1; (void)st;
     throw Error(PTF_EUNSUPPORTED, "built without NCCL");
 #endif
   }
+  int chunk_lo(int c) const { return (int)((long)nkx * c / n_chunks); }
 
   // ---------------- kernels ----------------
   YArgs zargs(int mode, double la, double lb, int llast) const {
@@ -190,12 +217,18 @@ class Fused3DEngine final : public Engine {
     a.yoff = (int)g.yoff;
     a.nzl = nzl;
     a.zsh = ilog2(nzl);
+    a.cid0 = 0;
+    a.cid_end = nkx * nyl;
     return a;
   }
 
   void run_z(bool has_in, int mode, double la = 0, double lb = 0, int llast = 0, int fam_override = -1,
-             bool unmasked = false) {
+             bool unmasked = false, int k0 = 0, int k1 = -1) {
     YArgs a = zargs(mode, la, lb, llast);
+    if (k1 >= 0) {
+      a.cid0 = k0 * nyl;
+      a.cid_end = k1 * nyl;
+    }
     if (unmasked) a.ax.dealias = 0;   // updatevars! transforms sol as it is stored (TAD.jl:815-821)
     int fam = (ctx.st.base == PTF_STEPPER_RK4) ? FAM_RK4 : (ctx.st.base == PTF_STEPPER_ETDRK4 ? FAM_ETD : FAM_OTHER);
     if (fam_override >= 0) fam = fam_override;
@@ -224,15 +257,25 @@ class Fused3DEngine final : public Engine {
     a.in_sr = (long long)blk - (long long)nyl * nzl;
     a.out_se = T * 8;                                    // [p][kr][zl/8][ll][zl%8]
     a.out_sr = (long long)blk - (long long)nyl * 8;
+    a.kr0 = 0;
+    a.nkr_launch = nkx;
     return a;
   }
-  void run_yinv() {
+  void run_yinv(int k0 = 0, int k1 = -1) {
     Y3Args a = y3args();
+    if (k1 >= 0) {
+      a.kr0 = k0;
+      a.nkr_launch = k1 - k0;
+    }
     PTF_DISPATCH_N3(ny, fused3_launch_y, true, &a, ctx.stream, n_sm);
     ++own_launches;
   }
-  void run_yfwd() {
+  void run_yfwd(int k0 = 0, int k1 = -1) {
     Y3Args a = y3args();
+    if (k1 >= 0) {
+      a.kr0 = k0;
+      a.nkr_launch = k1 - k0;
+    }
     PTF_DISPATCH_N3(ny, fused3_launch_y, false, &a, ctx.stream, n_sm);
     ++own_launches;
   }
@@ -274,14 +317,53 @@ class Fused3DEngine final : public Engine {
     ac_valid = true;
   }
 
+  // One stage.  Single GPU: yinv -> x -> yfwd -> z.  Slab-decomposed: the same with the two exchanges pipelined over
+  // kr chunks on the high-priority stream, so that chunk c travels while chunk c+1 is being computed:
+  //   main:  x | yfwd(0) yfwd(1) ... | z(0) z(1) ...            | (next stage) yinv(0) yinv(1) ... x
+  //   comm:      P^xy(0)  P^xy(1) ...  |  A,C(0)  A,C(1) ...
+  // The stage therefore starts with the y-inverse kernels of the chunks as they arrive.
   void stage(int mode, double la = 0, double lb = 0, int llast = 0) {
-    run_yinv();
+    if (!pipelined) {
+      run_yinv();
+      run_x();
+      run_yfwd();
+      exchange(PXY, RP);
+      run_z(true, mode, la, lb, llast);
+      exchange(ZA, RA);
+      exchange(ZC, RC);
+      return;
+    }
+    const int nc = n_chunks;
+    for (int c = 0; c < nc; ++c) {   // A, C chunks of the previous stage (or of the prologue) as they arrive
+      if (ac_in_flight) PTF_CUDA(cudaStreamWaitEvent(ctx.stream, ev[3][c], 0));
+      run_yinv(chunk_lo(c), chunk_lo(c + 1));
+    }
     run_x();
-    run_yfwd();
-    exchange(PXY, RP);
-    run_z(true, mode, la, lb, llast);
-    exchange(ZA, RA);
-    exchange(ZC, RC);
+    for (int c = 0; c < nc; ++c) {
+      const int k0 = chunk_lo(c), k1 = chunk_lo(c + 1);
+      run_yfwd(k0, k1);
+      PTF_CUDA(cudaEventRecord(ev[0][c], ctx.stream));
+      PTF_CUDA(cudaStreamWaitEvent(s_comm, ev[0][c], 0));
+      exchange(PXY, RP, k0, k1, s_comm);
+      PTF_CUDA(cudaEventRecord(ev[1][c], s_comm));
+    }
+    for (int c = 0; c < nc; ++c) {
+      const int k0 = chunk_lo(c), k1 = chunk_lo(c + 1);
+      PTF_CUDA(cudaStreamWaitEvent(ctx.stream, ev[1][c], 0));
+      run_z(true, mode, la, lb, llast, -1, false, k0, k1);
+      PTF_CUDA(cudaEventRecord(ev[2][c], ctx.stream));
+      PTF_CUDA(cudaStreamWaitEvent(s_comm, ev[2][c], 0));
+      exchange(ZA, RA, k0, k1, s_comm);
+      exchange(ZC, RC, k0, k1, s_comm);
+      PTF_CUDA(cudaEventRecord(ev[3][c], s_comm));
+    }
+    ac_in_flight = true;
+  }
+  // the main stream waits for the A, C exchanges still in flight on the comm stream (end of a step)
+  void join_exchanges() {
+    if (!ac_in_flight) return;
+    for (int c = 0; c < n_chunks; ++c) PTF_CUDA(cudaStreamWaitEvent(ctx.stream, ev[3][c], 0));
+    ac_in_flight = false;
   }
 
   // ---------------- boundary ----------------
@@ -379,6 +461,7 @@ class Fused3DEngine final : public Engine {
         stage(variant == 1 ? CM_AB3_EULER : CM_AB3);
         break;
     }
+    join_exchanges();   // a step (and a captured graph) ends with every exchange joined back into the step stream
   }
 
   void step_once(int64_t step_index) override {
@@ -449,11 +532,15 @@ class Fused3DEngine final : public Engine {
   }
 
   // Average device time of one of the four stage kernels over `reps` REAL RK4 steps (events around every launch of
-  // that kernel on the step stream).  The solution is backed up and restored, the clock is untouched.
+  // that kernel on the step stream; unpipelined sequence).  "exchange" = one field's all-to-all (three per stage),
+  // run alone on the stream, i.e. the time the collective costs when nothing hides it.
+  // The solution is backed up and restored, the clock is untouched.
   float time_kernel(const char* kname, int reps) override {
     std::string k(kname ? kname : "");
-    int which = k == "zkernel" ? 0 : k == "yinv" ? 1 : k == "xkernel" ? 2 : k == "yfwd" ? 3 : -1;
-    if (which < 0) throw Error(PTF_EINVAL, "fused 3-D engine: unknown kernel '" + k + "' (zkernel|yinv|xkernel|yfwd)");
+    int which = k == "zkernel" ? 0 : k == "yinv" ? 1 : k == "xkernel" ? 2 : k == "yfwd" ? 3 : k == "exchange" ? 4 : -1;
+    if (which < 0)
+      throw Error(PTF_EINVAL, "fused 3-D engine: unknown kernel '" + k + "' (zkernel|yinv|xkernel|yfwd|exchange)");
+    if (which == 4 && P == 1) throw Error(PTF_EUNSUPPORTED, "no exchange on a single GPU");
     if (ctx.st.base != PTF_STEPPER_RK4) throw Error(PTF_EUNSUPPORTED, "kernel timing is implemented for RK4 steps");
     DevBuf<double2> backup;
     backup.alloc(nspec);
@@ -461,39 +548,49 @@ class Fused3DEngine final : public Engine {
     refresh_separable();
     if (!ac_valid) prologue();
     const int modes[4] = {CM_RK4_S1, CM_RK4_S2, CM_RK4_S3, CM_RK4_S4};
-    std::vector<cudaEvent_t> ev(2 * 4 * reps);
-    for (auto& e : ev) PTF_CUDA(cudaEventCreate(&e));
-    auto one_step = [&](int rep, bool record) {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+    bool record = false;
+    auto timed = [&](int id, auto&& fn) {
+      const bool on = record && which == id;
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (on) {
+        PTF_CUDA(cudaEventCreate(&e0));
+        PTF_CUDA(cudaEventCreate(&e1));
+        PTF_CUDA(cudaEventRecord(e0, ctx.stream));
+      }
+      fn();
+      if (on) {
+        PTF_CUDA(cudaEventRecord(e1, ctx.stream));
+        evs.push_back({e0, e1});
+      }
+    };
+    auto one_step = [&]() {
       for (int s = 0; s < 4; ++s) {
-        int idx = 2 * (4 * rep + s);
-        auto timed = [&](int id, auto&& fn) {
-          if (record && which == id) PTF_CUDA(cudaEventRecord(ev[idx], ctx.stream));
-          fn();
-          if (record && which == id) PTF_CUDA(cudaEventRecord(ev[idx + 1], ctx.stream));
-        };
         timed(1, [&] { run_yinv(); });
         timed(2, [&] { run_x(); });
         timed(3, [&] { run_yfwd(); });
-        exchange(PXY, RP);
+        timed(4, [&] { exchange(PXY, RP); });
         timed(0, [&] { run_z(true, modes[s]); });
-        exchange(ZA, RA);
-        exchange(ZC, RC);
+        timed(4, [&] { exchange(ZA, RA); });
+        timed(4, [&] { exchange(ZC, RC); });
       }
     };
-    one_step(0, false);  // warm
-    for (int r = 0; r < reps; ++r) one_step(r, true);
+    one_step();  // warm
+    record = true;
+    for (int r = 0; r < reps; ++r) one_step();
     PTF_CUDA(cudaStreamSynchronize(ctx.stream));
     double total = 0;
-    for (int i = 0; i < 4 * reps; ++i) {
+    for (auto& e : evs) {
       float ms = 0;
-      PTF_CUDA(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+      PTF_CUDA(cudaEventElapsedTime(&ms, e.first, e.second));
       total += ms;
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
     }
-    for (auto& e : ev) cudaEventDestroy(e);
     PTF_CUDA(cudaMemcpyAsync(s0.p, backup.p, s0.bytes(), cudaMemcpyDeviceToDevice, ctx.stream));
     ac_valid = false;
     PTF_CUDA(cudaStreamSynchronize(ctx.stream));
-    return (float)(total / (4.0 * reps));
+    return (float)(total / (double)evs.size());
   }
 
  private:
@@ -510,6 +607,12 @@ class Fused3DEngine final : public Engine {
   bool sep_dirty = true;
   cufftHandle plan_fwd = 0, plan_inv = 0;
   bool ac_valid = false;
+  // pipelined slab exchange
+  static constexpr int MAXCH = 16;
+  int n_chunks = 1;
+  bool pipelined = false, ac_in_flight = false;
+  cudaStream_t s_comm = nullptr;
+  cudaEvent_t ev[4][MAXCH] = {};
   int n_sm = 148;
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
   int64_t per_step_own = 0, per_step_lib = 0;

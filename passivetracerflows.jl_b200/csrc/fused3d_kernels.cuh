@@ -38,6 +38,7 @@ struct Y3Args {
   // offset(e) = base(t) + e * s_e + (e >> esh) * s_r, all in double2 units (see y3_strides)
   int esh;
   long long in_se, in_sr, out_se, out_sr;
+  int kr0 = 0, nkr_launch = 0;   // this launch covers kr in [kr0, kr0 + nkr_launch): a chunk of the pipelined exchange
 };
 
 // ---- inverse y transforms of one pair of z planes (zl, zl+1) of one kr ----
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_yinv3(Y3Args a) {
   const int zp_raw = blockIdx.x * F + grp;
   const bool active = 2 * zp_raw < a.nzl;
   const int zl = active ? 2 * zp_raw : 0;
-  const int kr = blockIdx.y;
+  const int kr = a.kr0 + blockIdx.y;
   double2* sm = smem + grp * PADN;
   // element l = t + T*e of this (kr, zl) column in the received blocks [r][kr][ll][zl]
   const size_t ibase = ((size_t)kr * a.nyl + t) * a.nzl + zl;
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_yfwd3(Y3Args a) {
   const int zp_raw = blockIdx.x * F + grp;
   const bool active = 2 * zp_raw < a.nzl;
   const int zl = active ? 2 * zp_raw : 0;
-  const int kr = blockIdx.y;
+  const int kr = a.kr0 + blockIdx.y;
   double2* sm = smem + grp * PADN;
   // element l = t + T*e of this (kr, zl) column in the blocks to send [p][kr][zl/8][ll][zl%8]
   const size_t obase = (((size_t)kr * (a.nzl >> 3) + (zl >> 3)) * a.nyl + t) * 8 + (zl & 7);
@@ -313,7 +314,7 @@ template <int N, int NT>
 void launch_z3_nt(bool has_in, int fam, const YArgs& a, cudaStream_t st) {
   if constexpr (NT >= Cfg<N>::T) {
     constexpr int F = NT / Cfg<N>::T;
-    dim3 grid((a.nkr + F - 1) / F, 1, 1);
+    dim3 grid((a.cid_end - a.cid0 + F - 1) / F, 1, 1);
     const size_t sm = y_smem<N, NT>() + g_smem_pad;
     if (a.ax.dealias) {
       if (!has_in) k_fused_y<N, FAM_RK4, false, true, NT, true, true><<<grid, NT, sm, st>>>(a);
@@ -330,7 +331,7 @@ void launch_z3_nt(bool has_in, int fam, const YArgs& a, cudaStream_t st) {
 }
 template <int N>
 void launch_z3(bool has_in, int fam, const YArgs& a, cudaStream_t st, int n_sm) {
-  if (pick_nt3<N>(a.nkr, n_sm) == 128) launch_z3_nt<N, 128>(has_in, fam, a, st);
+  if (pick_nt3<N>(a.cid_end - a.cid0, n_sm) == 128) launch_z3_nt<N, 128>(has_in, fam, a, st);
   else launch_z3_nt<N, 64>(has_in, fam, a, st);
 }
 
@@ -351,11 +352,10 @@ void launch_x3(int vmode, const XArgs& a, int nplanes, cudaStream_t st, int n_sm
 }
 
 template <int N, int NT>
-void launch_y3_nt(bool inverse, const Y3Args& a, int kr0, int nkr_chunk, cudaStream_t st) {
+void launch_y3_nt(bool inverse, const Y3Args& a, cudaStream_t st) {
   if constexpr (NT >= Cfg<N>::T) {
     constexpr int F = NT / Cfg<N>::T;
-    (void)kr0;
-    dim3 grid((a.nzl / 2 + F - 1) / F, nkr_chunk, 1);
+    dim3 grid((a.nzl / 2 + F - 1) / F, a.nkr_launch, 1);
     const size_t sm = y_smem<N, NT>() + g_smem_pad;
     if (inverse) k_yinv3<N, NT><<<grid, NT, sm, st>>>(a);
     else k_yfwd3<N, NT><<<grid, NT, sm, st>>>(a);
@@ -363,8 +363,8 @@ void launch_y3_nt(bool inverse, const Y3Args& a, int kr0, int nkr_chunk, cudaStr
 }
 template <int N>
 void launch_y3(bool inverse, const Y3Args& a, cudaStream_t st, int n_sm) {
-  if (pick_nt3<N>((long)(a.nzl / 2) * a.nkx, n_sm) == 128) launch_y3_nt<N, 128>(inverse, a, 0, a.nkx, st);
-  else launch_y3_nt<N, 64>(inverse, a, 0, a.nkx, st);
+  if (pick_nt3<N>((long)(a.nzl / 2) * a.nkr_launch, n_sm) == 128) launch_y3_nt<N, 128>(inverse, a, st);
+  else launch_y3_nt<N, 64>(inverse, a, st);
 }
 
 }  // namespace

@@ -57,6 +57,7 @@ struct YArgs {
   int nkx = 0;                // nx/2+1
   int nyl = 1, yoff = 0;      // local ky rows of this rank's spectral slab and the global index of the first one
   int nzl = 0, zsh = 0;       // planes per rank (nz / P, a power of two) and log2 of it
+  int cid0 = 0, cid_end = 0;  // this launch covers columns [cid0, cid_end): a kr chunk of the pipelined slab exchange
 };
 
 enum { FAM_RK4 = 0, FAM_ETD = 1, FAM_OTHER = 2 };
@@ -267,8 +268,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
     t_w = t_nh + 64;
   }
   const int grp = threadIdx.x / T, t = threadIdx.x % T;
-  const int cid_raw = blockIdx.x * F + grp;
-  const bool active = cid_raw < a.nkr;
+  const int cid_raw = blockIdx.x * F + grp + (D3 ? a.cid0 : 0);
+  const bool active = cid_raw < (D3 ? a.cid_end : a.nkr);
   const int cid = active ? cid_raw : 0;
   const int b = blockIdx.y;
   double2* sm = smem + grp * PADN;

@@ -215,3 +215,14 @@ def test_fused3d_agrees_with_cufft_engine_256():
     assert rel_l2(pc.updatevars(), outs[0]) <= 5 * TOL_STEP
     pf.close()
     pc.close()
+
+
+@pytest.mark.parametrize("chunks", [2, 4, 7])
+def test_fused3d_chunked_pipeline_on_one_gpu(monkeypatch, chunks):
+    # the slab pipeline's chunked launch sequence (kr chunks, comm-stream events) with the exchange a no-op: same results
+    monkeypatch.setenv("PTF_F3_CHUNKS", str(chunks))
+    n, L = (64, 128, 64), (2 * np.pi, 4.0, 3.0)
+    vel, c0 = _abc(n, L, 0.5)
+    for stepper in ("RK4", "FilteredETDRK4", "LSRK54"):
+        kw = dict(n=n, L=L, kappa=(0.01, 0.02, 0.005), dt=2e-3, stepper=stepper, velocity=vel, steady=True)
+        _compare(kw, c0, [1, 3])
