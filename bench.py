@@ -255,15 +255,37 @@ def measure_slab3d(n, stepper, steps, warmup, rank, world, local_rank, P, barrie
         compute_ms = 4 * sum(v["ms"] for v in kern.values())
         out["compute_ms_per_step"] = compute_ms
         if world > 1:
-            ex_ms = max_over_ranks(prob.kernel_time_ms("exchange", 2))
             out_bytes = spec_l * (world - 1) / world    # what one field's all-to-all sends out of each GPU
-            serial = 12 * ex_ms
-            out["exchange"] = {"ms_per_field_alone": ex_ms, "fields_per_step": 12, "bytes_out_per_gpu_per_field": out_bytes,
-                               "alltoall_gbs_achieved": out_bytes / ex_ms / 1e6,
-                               "nvlink_frac_of_900": out_bytes / ex_ms / 1e6 / 900.0,
-                               "serial_ms_per_step": serial,
-                               "hidden_frac": max(0.0, min(1.0, 1.0 - max(0.0, step_ms - compute_ms) / serial)),
-                               "floor_ms_per_step_at_900GBs": 12 * out_bytes / 900e9 * 1e3}
+            floor = 12 * out_bytes / 900e9 * 1e3
+            try:
+                ex_ms = max_over_ranks(prob.kernel_time_ms("exchange", 2))
+                serial = 12 * ex_ms
+                out["exchange"] = {"mode": "NCCL send/recv, kr-chunked on a priority stream", "ms_per_field_alone": ex_ms,
+                                   "fields_per_step": 12, "bytes_out_per_gpu_per_field": out_bytes,
+                                   "alltoall_gbs_achieved": out_bytes / ex_ms / 1e6,
+                                   "nvlink_frac_of_900": out_bytes / ex_ms / 1e6 / 900.0,
+                                   "serial_ms_per_step": serial,
+                                   "hidden_frac": max(0.0, min(1.0, 1.0 - max(0.0, step_ms - compute_ms) / serial)),
+                                   "floor_ms_per_step_at_900GBs": floor}
+            except RuntimeError:
+                # P2P mode: the z-column kernel gathers P^xy from the peers and stores A, C into the peers' memory over
+                # NVLink (CUDA IPC), so the all-to-all has no launch of its own.  Its cost = how much longer that kernel
+                # runs than its share of the single-GPU kernel; its rate = the bytes it pushes out over its run time.
+                z_ms = kern["zkernel"]["ms"]
+                n1k = partitioned_n1_kernels(n)
+                z_share = None if n1k is None else n1k["zkernel"]["ms"] / world
+                exposed = None if z_share is None else 4 * max(0.0, z_ms - z_share)
+                out["exchange"] = {"mode": "P2P over NVLink fused into the z-column kernel (loads of the peers' P^xy, "
+                                           "stores into the peers' A, C; CUDA IPC + cross-GPU barrier kernel)",
+                                   "fields_per_step": 12, "bytes_out_per_gpu_per_field": out_bytes,
+                                   "z_kernel_ms": z_ms, "z_kernel_ms_single_gpu_share": z_share,
+                                   "alltoall_gbs_achieved": 2 * out_bytes / z_ms / 1e6,
+                                   "nvlink_frac_of_900": 2 * out_bytes / z_ms / 1e6 / 900.0,
+                                   "exposed_ms_per_step": exposed, "floor_ms_per_step_at_900GBs": floor,
+                                   "hidden_frac": None if exposed is None else max(0.0, min(1.0, 1.0 - exposed / floor)),
+                                   "note": "alltoall_gbs_achieved = bytes of A and C stored to peers by one launch / that "
+                                           "launch's whole run time (a lower bound: the kernel also does its local work); "
+                                           "hidden_frac = 1 - exposed / (12 fields at 900 GB/s)"}
     prob.close()
     return out, dev
 
@@ -298,6 +320,14 @@ def partitioned_n1_reference(n):
     except Exception:
         pass
     return None, None
+
+
+def partitioned_n1_kernels(n):
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_partitioned_n1.json")))
+        return d["kernels"] if d.get("n") == n else None
+    except Exception:
+        return None
 
 
 def run_partitioned(args, rank, world, local_rank, P, barrier, max_over_ranks):

@@ -187,7 +187,7 @@ class FusedEngine final : public Engine {
 
   // ---------------- the two hot kernels ----------------
   YArgs yargs(int mode, double la, double lb, int llast) const {
-    YArgs a;
+    YArgs a{};
     a.Px = Px.p;
     a.A = A.p;
     a.Bf = Bf.p;

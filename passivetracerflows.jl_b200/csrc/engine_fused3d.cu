@@ -66,9 +66,27 @@ class Fused3DEngine final : public Engine {
     if (base == PTF_STEPPER_ETDRK4) zalloc(s2);
     if (base != PTF_STEPPER_FORWARD_EULER) zalloc(acc);
     if (base == PTF_STEPPER_ETDRK4 || base == PTF_STEPPER_AB3) zalloc(n1);
-    for (auto* b : {&U1, &U2, &U3, &U4, &YA, &YB, &YC}) zalloc(*b);
+    // Exchange mode for P > 1: peer-to-peer over NVLink (the z-column kernel gathers P^xy from the peers' send
+    // buffers and stores A, C into the peers' receive buffers; CUDA IPC, no collective call on the step path), or
+    // NCCL send/recv pipelined over kr chunks when PTF_F3_P2P=0 or the peers cannot be mapped.
+    {
+      const char* pe = std::getenv("PTF_F3_P2P");
+      want_p2p = P > 1 && !(pe && std::atoi(pe) == 0);
+    }
+    for (auto* b : {&U1, &U3, &U4, &YA, &YB, &YC}) zalloc(*b);
+    if (want_p2p) {
+      try {
+        setup_p2p();
+      } catch (const Error& e) {
+        fprintf(stderr, "libptf_b200: P2P slab exchange unavailable (%s); using the NCCL pipeline\n", e.what());
+        p2p = false;
+      }
+    }
+    if (!p2p) zalloc(U2);
     if (P == 1) {
       ZA = U1.p; ZC = U2.p; RA = U1.p; RC = U2.p; PX = U3.p; PXY = U4.p; RP = U4.p;
+    } else if (p2p) {   // PXY: local send buffer the peers read; RA, RC: receive buffers the peers write
+      PXY = U1.p; RA = U3.p; RC = U4.p; PX = U3.p; ZA = nullptr; ZC = nullptr; RP = nullptr;
     } else {
       ZA = U1.p; ZC = U2.p; RA = U3.p; RC = U4.p; PX = U3.p; PXY = U1.p; RP = U4.p;
     }
@@ -95,8 +113,10 @@ class Fused3DEngine final : public Engine {
     // pipelined exchange: kr chunks, exchanges on a high-priority stream overlapping the column kernels.
     // PTF_F3_CHUNKS = number of chunks (default 4); on one GPU it switches the chunked launch sequence on as a test
     // hook (every kernel launch and event of the slab pipeline, with the exchange itself a no-op).
+    if (std::getenv("PTF_NO_GRAPH")) ctx.d.use_graph = 0;   // experiment knob: eager launches instead of a captured graph
     const char* ce = std::getenv("PTF_F3_CHUNKS");
-    pipelined = P > 1 || (ce && std::atoi(ce) > 1);
+    pipelined = (P > 1 && !p2p) || (P == 1 && ce && std::atoi(ce) > 1);
+    if (P > 1 && !p2p) ctx.d.use_graph = 0;   // measured: the captured multi-stream NCCL pipeline runs 15 % slower
     if (pipelined) {
       n_chunks = 4;
       if (ce) {
@@ -115,6 +135,7 @@ class Fused3DEngine final : public Engine {
 
   ~Fused3DEngine() override {
     drop_graphs();
+    teardown_p2p();
     if (s_comm) cudaStreamDestroy(s_comm);
     for (auto& row : ev)
       for (auto& e : row)
@@ -164,7 +185,7 @@ class Fused3DEngine final : public Engine {
   // ---------------- the exchange between the y- and z-column kernels (the only collective) ----------------
   // kr range [k0, k1) of every peer block (the whole block by default) on stream `st`
   void exchange(const double2* send, double2* recv, int k0 = 0, int k1 = -1, cudaStream_t st = nullptr) {
-    if (P == 1) return;  // send and recv are the same buffer
+    if (P == 1 || p2p) return;  // same buffer / the z-column kernel moved the data itself
 #ifdef PTF_WITH_NCCL
     if (k1 < 0) k1 = nkx;
     if (!st) st = ctx.stream;
@@ -219,7 +240,111 @@ class Fused3DEngine final : public Engine {
     a.zsh = ilog2(nzl);
     a.cid0 = 0;
     a.cid_end = nkx * nyl;
+    for (int r = 0; r < 16; ++r) {
+      a.Psrc[r] = nullptr;
+      a.Adst[r] = nullptr;
+      a.Cdst[r] = nullptr;
+    }
+    for (int r = 0; r < P; ++r) {
+      if (p2p) {   // block (r -> me) of r's send buffer; block (me -> r) of r's receive buffers
+        a.Psrc[r] = pxy_peer[r] + (size_t)rank * blk;
+        a.Adst[r] = ra_peer[r] + (size_t)rank * blk;
+        a.Cdst[r] = rc_peer[r] + (size_t)rank * blk;
+      } else {
+        a.Psrc[r] = RP + (size_t)r * blk;
+        a.Adst[r] = ZA + (size_t)r * blk;
+        a.Cdst[r] = ZC + (size_t)r * blk;
+      }
+    }
     return a;
+  }
+
+  // ---------------- P2P exchange: peers' buffers mapped with CUDA IPC, cross-GPU barrier kernel ----------------
+  void setup_p2p() {
+#ifdef PTF_WITH_NCCL
+    ncclComm_t comm = (ncclComm_t)ctx.nccl_comm;
+    flags.alloc(32, &dev_bytes);
+    PTF_CUDA(cudaMemsetAsync(flags.p, 0, flags.bytes(), ctx.stream));
+    struct Handles { cudaIpcMemHandle_t h[4]; };
+    static_assert(sizeof(Handles) == 256, "IPC handle size");
+    Handles mine;
+    PTF_CUDA(cudaIpcGetMemHandle(&mine.h[0], U1.p));
+    PTF_CUDA(cudaIpcGetMemHandle(&mine.h[1], U3.p));
+    PTF_CUDA(cudaIpcGetMemHandle(&mine.h[2], U4.p));
+    PTF_CUDA(cudaIpcGetMemHandle(&mine.h[3], flags.p));
+    DevBuf<unsigned char> hb;
+    hb.alloc((size_t)P * sizeof(Handles));
+    PTF_CUDA(cudaMemcpyAsync(hb.p + (size_t)rank * sizeof(Handles), &mine, sizeof(Handles), cudaMemcpyHostToDevice,
+                             ctx.stream));
+    ncclResult_t r = ncclAllGather(hb.p + (size_t)rank * sizeof(Handles), hb.p, sizeof(Handles), ncclUint8, comm,
+                                   ctx.stream);
+    if (r != ncclSuccess) throw Error(PTF_ENCCL, std::string("ncclAllGather(IPC handles): ") + ncclGetErrorString(r));
+    std::vector<Handles> all(P);
+    PTF_CUDA(cudaMemcpyAsync(all.data(), hb.p, (size_t)P * sizeof(Handles), cudaMemcpyDeviceToHost, ctx.stream));
+    PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+    int ok = 1;
+    for (int q = 0; q < P && ok; ++q) {
+      if (q == rank) {
+        pxy_peer[q] = U1.p; ra_peer[q] = U3.p; rc_peer[q] = U4.p; flag_peer[q] = flags.p;
+        continue;
+      }
+      void* ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+      for (int i = 0; i < 4; ++i) {
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr[i], all[q].h[i], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+          cudaGetLastError();
+          ok = 0;
+          break;
+        }
+        opened.push_back(ptr[i]);
+      }
+      if (!ok) break;
+      pxy_peer[q] = (const double2*)ptr[0];
+      ra_peer[q] = (double2*)ptr[1];
+      rc_peer[q] = (double2*)ptr[2];
+      flag_peer[q] = (unsigned*)ptr[3];
+    }
+    // all ranks must agree (a rank that failed to map a peer would otherwise wait for barriers nobody joins)
+    DevBuf<int> agree;
+    agree.alloc(1);
+    PTF_CUDA(cudaMemcpyAsync(agree.p, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
+    ncclAllReduce(agree.p, agree.p, 1, ncclInt, ncclMin, comm, ctx.stream);
+    PTF_CUDA(cudaMemcpyAsync(&ok, agree.p, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (!ok) {
+      for (void* q : opened) cudaIpcCloseMemHandle(q);
+      opened.clear();
+      throw Error(PTF_EUNSUPPORTED, "cudaIpcOpenMemHandle failed on at least one rank");
+    }
+    p2p = true;
+#else
+    throw Error(PTF_EUNSUPPORTED, "built without NCCL");
+#endif
+  }
+  void teardown_p2p() {
+    if (!p2p) return;
+#ifdef PTF_WITH_NCCL
+    cudaStreamSynchronize(ctx.stream);
+    for (void* q : opened) cudaIpcCloseMemHandle(q);
+    opened.clear();
+    // nobody frees a buffer a peer may still have mapped: one tiny collective as a host-level barrier
+    ncclComm_t comm = (ncclComm_t)ctx.nccl_comm;
+    DevBuf<int> t;
+    t.alloc(1);
+    cudaMemsetAsync(t.p, 0, sizeof(int), ctx.stream);
+    ncclAllReduce(t.p, t.p, 1, ncclInt, ncclSum, comm, ctx.stream);
+    cudaStreamSynchronize(ctx.stream);
+#endif
+    p2p = false;
+  }
+  void xbarrier() {
+    if (!p2p) return;
+    XbArgs a;
+    for (int q = 0; q < 16; ++q) a.peer[q] = q < P ? flag_peer[q] : nullptr;
+    a.me = rank;
+    a.P = P;
+    k_xbarrier<<<1, 32, 0, ctx.stream>>>(flags.p, a);
+    ++own_launches;
   }
 
   void run_z(bool has_in, int mode, double la = 0, double lb = 0, int llast = 0, int fam_override = -1,
@@ -232,8 +357,12 @@ class Fused3DEngine final : public Engine {
     if (unmasked) a.ax.dealias = 0;   // updatevars! transforms sol as it is stored (TAD.jl:815-821)
     int fam = (ctx.st.base == PTF_STEPPER_RK4) ? FAM_RK4 : (ctx.st.base == PTF_STEPPER_ETDRK4 ? FAM_ETD : FAM_OTHER);
     if (fam_override >= 0) fam = fam_override;
+    // P2P mode: this kernel reads the peers' P^xy and writes the peers' A, C.  Barrier before: every rank has finished
+    // writing its P^xy and reading its previous A, C.  Barrier after: all A, C have landed, all P^xy reads are done.
+    xbarrier();
     PTF_DISPATCH_N3(nz, fused3_launch_z, has_in, fam, &a, ctx.stream, n_sm);
     ++own_launches;
+    xbarrier();
   }
 
   Y3Args y3args() const {
@@ -541,6 +670,8 @@ class Fused3DEngine final : public Engine {
     if (which < 0)
       throw Error(PTF_EINVAL, "fused 3-D engine: unknown kernel '" + k + "' (zkernel|yinv|xkernel|yfwd|exchange)");
     if (which == 4 && P == 1) throw Error(PTF_EUNSUPPORTED, "no exchange on a single GPU");
+    if (which == 4 && p2p)
+      throw Error(PTF_EUNSUPPORTED, "P2P mode: the exchange is fused into the z-column kernel's loads and stores");
     if (ctx.st.base != PTF_STEPPER_RK4) throw Error(PTF_EUNSUPPORTED, "kernel timing is implemented for RK4 steps");
     DevBuf<double2> backup;
     backup.alloc(nspec);
@@ -607,7 +738,15 @@ class Fused3DEngine final : public Engine {
   bool sep_dirty = true;
   cufftHandle plan_fwd = 0, plan_inv = 0;
   bool ac_valid = false;
-  // pipelined slab exchange
+  // P2P slab exchange (CUDA IPC over NVLink)
+  bool want_p2p = false, p2p = false;
+  DevBuf<unsigned> flags;            // [0..15] peers' epochs, [16] own barrier count
+  std::vector<void*> opened;
+  const double2* pxy_peer[16] = {};
+  double2* ra_peer[16] = {};
+  double2* rc_peer[16] = {};
+  unsigned* flag_peer[16] = {};
+  // pipelined slab exchange (NCCL mode)
   static constexpr int MAXCH = 16;
   int n_chunks = 1;
   bool pipelined = false, ac_in_flight = false;

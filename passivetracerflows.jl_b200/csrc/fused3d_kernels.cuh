@@ -188,6 +188,37 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_yfwd3(Y3Args a) {
   tmem::free_cta<TCOLS>(tbase);
 }
 
+// ---- cross-GPU barrier of the P2P slab exchange (one process per GPU, peers' flag words mapped through CUDA IPC) ----
+// Every rank bumps its epoch counter, publishes the epoch in slot `me` of every peer's flag array (release, system
+// scope) and waits until all peers have published theirs here (acquire).  Stream order puts it after the kernel whose
+// peer stores / loads it fences.  A rank that never arrives (crashed peer) trips the time-out instead of hanging the GPU.
+struct XbArgs {
+  unsigned* peer[16];   // [p]: rank p's flag array (own array for p == me)
+  int me, P;
+};
+__global__ void __launch_bounds__(32) k_xbarrier(unsigned* __restrict__ local, XbArgs a) {
+  __shared__ unsigned epoch_s;
+  if (threadIdx.x == 0) epoch_s = ++local[16];   // slot 16: this rank's barrier count (same sequence on every rank)
+  __syncthreads();
+  const unsigned epoch = epoch_s;
+  const int p = threadIdx.x;
+  if (p < a.P) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer[p] + a.me), "r"(epoch) : "memory");
+    unsigned v;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local + p) : "memory");
+      if (clock64() - t0 > 40000000000LL) {   // ~20 s: a peer is gone
+        printf("libptf_b200: cross-GPU barrier timed out (rank %d waiting for rank %d, epoch %u, saw %u)\n", a.me, p,
+               epoch, v);
+        __trap();
+      }
+    } while ((int)(v - epoch) < 0);
+    __threadfence_system();
+  }
+}
+
 // ---- separable flows (PTF_FLOW_SEPARABLE): u_a = sum_m a_m(t) X_m(x) Y_m(y) Z_m(z) written out once per step ----
 // The velocity is frozen at clock.t for all stages of a step (TAD.jl:737), so the three fields are evaluated ONCE per
 // step (24 B/pt, ~4 % of a step's traffic) and the row kernel reads them like steady arrays; evaluating the sums

@@ -58,6 +58,13 @@ struct YArgs {
   int nyl = 1, yoff = 0;      // local ky rows of this rank's spectral slab and the global index of the first one
   int nzl = 0, zsh = 0;       // planes per rank (nz / P, a power of two) and log2 of it
   int cid0 = 0, cid_end = 0;  // this launch covers columns [cid0, cid_end): a kr chunk of the pipelined slab exchange
+  // Where the blocks of the slab exchange live, per rank (P <= 16).  NCCL / single GPU: slices of this rank's own
+  // send / receive buffers.  P2P mode: pointers into the PEERS' memory (CUDA IPC over NVLink) — the kernel gathers
+  // rank r's P^xy block straight from r's send buffer and stores A, C straight into rank p's receive buffers, so the
+  // all-to-all is fused into this kernel's loads and stores.
+  const double2* Psrc[16];    // [r]: block (r -> this rank) of P^xy, [kr][zl/8][ll][zl%8]
+  double2* Adst[16];          // [p]: block (this rank -> p) of A, [kr][ll][zl]
+  double2* Cdst[16];          // [p]: same for C
 };
 
 enum { FAM_RK4 = 0, FAM_ETD = 1, FAM_OTHER = 2 };
@@ -305,13 +312,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
   if (HAS_IN) {
     double2 v[16];
     if (D3) {
-      // P^xy blocks as received: [r][kr][zl/8][ll][zl%8]; 8 consecutive z of one column are one 128-byte line
-      const size_t blk = (size_t)a.nkx * (a.nzl >> 3) * a.nyl * 8;   // one rank's block
-      const double2* P = a.Px + ((size_t)c.kr * (a.nzl >> 3) * a.nyl + ll) * 8;
+      // P^xy block of rank r = z / nzl: [kr][zl/8][ll][zl%8]; 8 consecutive z of one column are one 128-byte line
+      const size_t pin = ((size_t)c.kr * (a.nzl >> 3) * a.nyl + ll) * 8;
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int z = t + T * e, r = z >> a.zsh, zl = z & (a.nzl - 1);
-        v[e] = __ldcg(P + (size_t)r * blk + (size_t)(zl >> 3) * a.nyl * 8 + (zl & 7));
+        v[e] = __ldcg(a.Psrc[r] + pin + (size_t)(zl >> 3) * a.nyl * 8 + (zl & 7));
       }
     } else {
       // P^x is stored blocked, [b][y/8][kr][y%8]: 8 consecutive y of one column are one 128-byte line, so this
@@ -409,15 +415,15 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
     return;
   }
 
-  // where element l of this column goes in A / B: contiguous in 2-D; 3-D: the block of the rank that owns plane l
-  auto out_off = [&](int l) -> size_t {
-    if (D3) return (((size_t)(l >> a.zsh) * a.nkr + cid) << a.zsh) + (l & (a.nzl - 1));
-    return col + l;
+  // where element l of this column goes in A / B: contiguous in 2-D; 3-D: the block of the rank p that owns plane l
+  auto out_ptr = [&](double2* base2d, double2* const* dst3d, int l) -> double2* {
+    if (D3) return dst3d[l >> a.zsh] + ((size_t)cid << a.zsh) + (l & (a.nzl - 1));
+    return base2d + col + l;
   };
   fft::fft_cta<NY, +1>(w, sm, t, a.tw);
   if (active) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) __stcg(a.A + out_off(t + T * e), w[out_slot<NY>(e)]);
+    for (int e = 0; e < 16; ++e) __stcg(out_ptr(a.A, a.Adst, t + T * e), w[out_slot<NY>(e)]);
   }
   // derivative along the transform axis: i*l*s'  (3-D: i*m*s')
   if (USE_TMEM) {  // s'/N is still parked in TMEM: no second trip to global memory
@@ -444,7 +450,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
   fft::fft_cta<NY, +1>(w, sm, t, a.tw);
   if (active) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) __stcg(a.Bf + out_off(t + T * e), w[out_slot<NY>(e)]);
+    for (int e = 0; e < 16; ++e) __stcg(out_ptr(a.Bf, a.Cdst, t + T * e), w[out_slot<NY>(e)]);
   }
   if (USE_TMEM) tmem::free_cta<TCOLS>(tbase);
 }
