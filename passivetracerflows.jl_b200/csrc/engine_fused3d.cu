@@ -82,11 +82,12 @@ class Fused3DEngine final : public Engine {
         p2p = false;
       }
     }
-    if (!p2p) zalloc(U2);
+    zalloc(U2);
     if (P == 1) {
       ZA = U1.p; ZC = U2.p; RA = U1.p; RC = U2.p; PX = U3.p; PXY = U4.p; RP = U4.p;
-    } else if (p2p) {   // PXY: local send buffer the peers read; RA, RC: receive buffers the peers write
-      PXY = U1.p; RA = U3.p; RC = U4.p; PX = U3.p; ZA = nullptr; ZC = nullptr; RP = nullptr;
+    } else if (p2p) {   // PXY: local send buffer the peers read; RA, RC: receive buffers the peers write; P^x has its
+                        // own buffer: a peer's z kernel may store chunk c of A while chunk c+1 of P^x is still being read
+      PXY = U1.p; RA = U3.p; RC = U4.p; PX = U2.p; ZA = nullptr; ZC = nullptr; RP = nullptr;
     } else {
       ZA = U1.p; ZC = U2.p; RA = U3.p; RC = U4.p; PX = U3.p; PXY = U1.p; RP = U4.p;
     }
@@ -115,7 +116,7 @@ class Fused3DEngine final : public Engine {
     // hook (every kernel launch and event of the slab pipeline, with the exchange itself a no-op).
     if (std::getenv("PTF_NO_GRAPH")) ctx.d.use_graph = 0;   // experiment knob: eager launches instead of a captured graph
     const char* ce = std::getenv("PTF_F3_CHUNKS");
-    pipelined = (P > 1 && !p2p) || (P == 1 && ce && std::atoi(ce) > 1);
+    pipelined = P > 1 || (ce && std::atoi(ce) > 1);
     if (P > 1 && !p2p) ctx.d.use_graph = 0;   // measured: the captured multi-stream NCCL pipeline runs 15 % slower
     if (pipelined) {
       n_chunks = 4;
@@ -124,6 +125,8 @@ class Fused3DEngine final : public Engine {
         if (c >= 1 && c <= MAXCH) n_chunks = c;
       }
       if (n_chunks > nkx) n_chunks = nkx;
+      if (n_chunks == 1 && P > 1 && p2p) pipelined = false;
+      if (const char* ze = std::getenv("PTF_F3_ZCTAS")) z_ctas = std::atoi(ze);   // 0 = full-size grid
       int lo = 0, hi = 0;
       PTF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
       PTF_CUDA(cudaStreamCreateWithPriority(&s_comm, cudaStreamNonBlocking, hi));
@@ -337,32 +340,35 @@ class Fused3DEngine final : public Engine {
 #endif
     p2p = false;
   }
-  void xbarrier() {
+  void xbarrier(cudaStream_t st = nullptr) {
     if (!p2p) return;
+    if (!st) st = ctx.stream;
     XbArgs a;
     for (int q = 0; q < 16; ++q) a.peer[q] = q < P ? flag_peer[q] : nullptr;
     a.me = rank;
     a.P = P;
-    k_xbarrier<<<1, 32, 0, ctx.stream>>>(flags.p, a);
+    k_xbarrier<<<1, 32, 0, st>>>(flags.p, a);
     ++own_launches;
   }
 
   void run_z(bool has_in, int mode, double la = 0, double lb = 0, int llast = 0, int fam_override = -1,
-             bool unmasked = false, int k0 = 0, int k1 = -1) {
+             bool unmasked = false, int k0 = 0, int k1 = -1, cudaStream_t st = nullptr, int grid_cap = 0) {
+    if (!st) st = ctx.stream;
     YArgs a = zargs(mode, la, lb, llast);
     if (k1 >= 0) {
       a.cid0 = k0 * nyl;
       a.cid_end = k1 * nyl;
     }
+    a.grid_cap = grid_cap;
     if (unmasked) a.ax.dealias = 0;   // updatevars! transforms sol as it is stored (TAD.jl:815-821)
     int fam = (ctx.st.base == PTF_STEPPER_RK4) ? FAM_RK4 : (ctx.st.base == PTF_STEPPER_ETDRK4 ? FAM_ETD : FAM_OTHER);
     if (fam_override >= 0) fam = fam_override;
     // P2P mode: this kernel reads the peers' P^xy and writes the peers' A, C.  Barrier before: every rank has finished
     // writing its P^xy and reading its previous A, C.  Barrier after: all A, C have landed, all P^xy reads are done.
-    xbarrier();
-    PTF_DISPATCH_N3(nz, fused3_launch_z, has_in, fam, &a, ctx.stream, n_sm);
+    xbarrier(st);
+    PTF_DISPATCH_N3(nz, fused3_launch_z, has_in, fam, &a, st, n_sm);
     ++own_launches;
-    xbarrier();
+    xbarrier(st);
   }
 
   Y3Args y3args() const {
@@ -468,6 +474,21 @@ class Fused3DEngine final : public Engine {
       run_yinv(chunk_lo(c), chunk_lo(c + 1));
     }
     run_x();
+    if (p2p) {
+      // P2P mode: the z-column kernel of chunk c (NVLink-bound: it reads the peers' P^xy and writes the peers' A, C)
+      // runs on the priority stream next to the HBM-bound y kernels of the other chunks on the main stream.
+      for (int c = 0; c < nc; ++c) {
+        const int k0 = chunk_lo(c), k1 = chunk_lo(c + 1);
+        run_yfwd(k0, k1);
+        PTF_CUDA(cudaEventRecord(ev[0][c], ctx.stream));
+        PTF_CUDA(cudaStreamWaitEvent(s_comm, ev[0][c], 0));
+        // barrier, kernel, barrier on the priority stream; a small persistent grid (z_ctas CTAs per SM)
+        run_z(true, mode, la, lb, llast, -1, false, k0, k1, s_comm, z_ctas * n_sm);
+        PTF_CUDA(cudaEventRecord(ev[3][c], s_comm));
+      }
+      ac_in_flight = true;
+      return;
+    }
     for (int c = 0; c < nc; ++c) {
       const int k0 = chunk_lo(c), k1 = chunk_lo(c + 1);
       run_yfwd(k0, k1);
@@ -479,7 +500,9 @@ class Fused3DEngine final : public Engine {
     for (int c = 0; c < nc; ++c) {
       const int k0 = chunk_lo(c), k1 = chunk_lo(c + 1);
       PTF_CUDA(cudaStreamWaitEvent(ctx.stream, ev[1][c], 0));
-      run_z(true, mode, la, lb, llast, -1, false, k0, k1);
+      // (single-GPU test hook: PTF_F3_ZCTAS also caps this launch, exercising the persistent grid-stride path)
+      run_z(true, mode, la, lb, llast, -1, false, k0, k1, nullptr,
+            (P == 1 && std::getenv("PTF_F3_ZCTAS")) ? z_ctas * n_sm : 0);
       PTF_CUDA(cudaEventRecord(ev[2][c], ctx.stream));
       PTF_CUDA(cudaStreamWaitEvent(s_comm, ev[2][c], 0));
       exchange(ZA, RA, k0, k1, s_comm);
@@ -748,7 +771,7 @@ class Fused3DEngine final : public Engine {
   unsigned* flag_peer[16] = {};
   // pipelined slab exchange (NCCL mode)
   static constexpr int MAXCH = 16;
-  int n_chunks = 1;
+  int n_chunks = 1, z_ctas = 1;
   bool pipelined = false, ac_in_flight = false;
   cudaStream_t s_comm = nullptr;
   cudaEvent_t ev[4][MAXCH] = {};

@@ -346,6 +346,7 @@ void launch_z3_nt(bool has_in, int fam, const YArgs& a, cudaStream_t st) {
   if constexpr (NT >= Cfg<N>::T) {
     constexpr int F = NT / Cfg<N>::T;
     dim3 grid((a.cid_end - a.cid0 + F - 1) / F, 1, 1);
+    if (a.grid_cap > 0 && (int)grid.x > a.grid_cap) grid.x = a.grid_cap;
     const size_t sm = y_smem<N, NT>() + g_smem_pad;
     if (a.ax.dealias) {
       if (!has_in) k_fused_y<N, FAM_RK4, false, true, NT, true, true><<<grid, NT, sm, st>>>(a);

@@ -58,6 +58,7 @@ struct YArgs {
   int nyl = 1, yoff = 0;      // local ky rows of this rank's spectral slab and the global index of the first one
   int nzl = 0, zsh = 0;       // planes per rank (nz / P, a power of two) and log2 of it
   int cid0 = 0, cid_end = 0;  // this launch covers columns [cid0, cid_end): a kr chunk of the pipelined slab exchange
+  int grid_cap = 0;           // host side only: > 0 = launch at most this many (persistent, grid-striding) CTAs
   // Where the blocks of the slab exchange live, per rank (P <= 16).  NCCL / single GPU: slices of this rank's own
   // send / receive buffers.  P2P mode: pointers into the PEERS' memory (CUDA IPC over NVLink) — the kernel gathers
   // rank r's P^xy block straight from r's send buffer and stores A, C straight into rank p's receive buffers, so the
@@ -252,30 +253,13 @@ __device__ __forceinline__ void etd_stage(const YArgs& a, const double2 (&v)[16]
 // D3 = z-column kernel of the fused 3-D engine (engine_fused3d.cu): column = (kr, local ky row), transform axis z,
 //      input P^xy gathered from [r][kr][zl/8][ll][zl%8] (r = z / nzl: the block received from rank r), outputs
 //      A = IFFT_z(s'), C = IFFT_z(i*m*s') written as [p][kr][ll][zl] (p = z / nzl: the block sent to rank p).
-template <int NY, int FAM, bool HAS_IN, bool HAS_OUT, int NT, bool DM = false, bool D3 = false>
-__global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
+// One column of the column kernel (all threads of the CTA call it together: the transforms contain CTA barriers).
+template <int NY, int FAM, bool HAS_IN, bool HAS_OUT, int NT, bool DM, bool D3>
+__device__ __forceinline__ void fused_y_column(const YArgs& a, const int cid_raw, const int grp, const int t,
+                                               double2* __restrict__ smem, const uint32_t t_nh, const uint32_t t_w) {
   constexpr int T = Cfg<NY>::T, F = NT / T, PADN = Cfg<NY>::PADN;
-  constexpr int TCOLS = NT > 128 ? 256 : 128;
-  static_assert(NT >= T && NT % T == 0, "CTA must hold whole transforms");
-  constexpr bool USE_TMEM = HAS_IN && FAM == FAM_RK4;   // N^ and s' parked in TMEM (see rk4_stage)
-  extern __shared__ double2 smem[];
-  // De-phase the two CTAs resident on each SM: without this every first-wave CTA starts at the same instant and the
-  // whole chip alternates between memory phases (FP64 idle) and FFT phases (HBM idle) in lock-step.
-  if (a.stagger > 0 && (int)(blockIdx.x + gridDim.x * blockIdx.y) < a.first_wave && (blockIdx.x & 1)) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < a.stagger) {
-    }
-  }
-
-  __shared__ uint32_t tslot;
-  uint32_t tbase = 0, t_nh = 0, t_w = 0;
-  if (USE_TMEM) {
-    tbase = tmem::alloc_cta<TCOLS>(&tslot);
-    t_nh = tmem::warp_addr(tbase, 128);
-    t_w = t_nh + 64;
-  }
-  const int grp = threadIdx.x / T, t = threadIdx.x % T;
-  const int cid_raw = blockIdx.x * F + grp + (D3 ? a.cid0 : 0);
+  constexpr bool USE_TMEM = HAS_IN && FAM == FAM_RK4;
+  (void)F;
   const bool active = cid_raw < (D3 ? a.cid_end : a.nkr);
   const int cid = active ? cid_raw : 0;
   const int b = blockIdx.y;
@@ -410,10 +394,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
       w[e] = make_double2(s.x * a.inv_n, s.y * a.inv_n);
     }
   }
-  if (!HAS_OUT) {
-    if (USE_TMEM) tmem::free_cta<TCOLS>(tbase);
-    return;
-  }
+  if (!HAS_OUT) return;
 
   // where element l of this column goes in A / B: contiguous in 2-D; 3-D: the block of the rank p that owns plane l
   auto out_ptr = [&](double2* base2d, double2* const* dst3d, int l) -> double2* {
@@ -451,6 +432,44 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
   if (active) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) __stcg(out_ptr(a.Bf, a.Cdst, t + T * e), w[out_slot<NY>(e)]);
+  }
+}
+
+template <int NY, int FAM, bool HAS_IN, bool HAS_OUT, int NT, bool DM = false, bool D3 = false>
+__global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
+  constexpr int T = Cfg<NY>::T, F = NT / T, PADN = Cfg<NY>::PADN;
+  constexpr int TCOLS = NT > 128 ? 256 : 128;
+  static_assert(NT >= T && NT % T == 0, "CTA must hold whole transforms");
+  constexpr bool USE_TMEM = HAS_IN && FAM == FAM_RK4;   // N^ and s' parked in TMEM (see rk4_stage)
+  extern __shared__ double2 smem[];
+  // De-phase the two CTAs resident on each SM: without this every first-wave CTA starts at the same instant and the
+  // whole chip alternates between memory phases (FP64 idle) and FFT phases (HBM idle) in lock-step.
+  if (a.stagger > 0 && (int)(blockIdx.x + gridDim.x * blockIdx.y) < a.first_wave && (blockIdx.x & 1)) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < a.stagger) {
+    }
+  }
+
+  __shared__ uint32_t tslot;
+  uint32_t tbase = 0, t_nh = 0, t_w = 0;
+  if (USE_TMEM) {
+    tbase = tmem::alloc_cta<TCOLS>(&tslot);
+    t_nh = tmem::warp_addr(tbase, 128);
+    t_w = t_nh + 64;
+  }
+  const int grp = threadIdx.x / T, t = threadIdx.x % T;
+  if (D3) {
+    // 3-D: grid-stride over the columns of this launch.  With a full-size grid every CTA takes one group of columns;
+    // the slab pipeline launches a SMALL persistent grid instead, so that this NVLink-bound kernel leaves most CTA
+    // slots of every SM to the HBM-bound kernels running next to it on the main stream.
+    for (int base = blockIdx.x * F + a.cid0; base < a.cid_end; base += gridDim.x * F) {
+      fused_y_column<NY, FAM, HAS_IN, HAS_OUT, NT, DM, D3>(a, base + grp, grp, t, smem, t_nh, t_w);
+      if (USE_TMEM) asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncthreads();   // the transform buffers and the TMEM parking slots are reused by the next column
+      if (USE_TMEM) asm volatile("tcgen05.fence::after_thread_sync;");
+    }
+  } else {
+    fused_y_column<NY, FAM, HAS_IN, HAS_OUT, NT, DM, D3>(a, blockIdx.x * F + grp, grp, t, smem, t_nh, t_w);
   }
   if (USE_TMEM) tmem::free_cta<TCOLS>(tbase);
 }

@@ -217,10 +217,13 @@ def test_fused3d_agrees_with_cufft_engine_256():
     pc.close()
 
 
-@pytest.mark.parametrize("chunks", [2, 4, 7])
-def test_fused3d_chunked_pipeline_on_one_gpu(monkeypatch, chunks):
-    # the slab pipeline's chunked launch sequence (kr chunks, comm-stream events) with the exchange a no-op: same results
+@pytest.mark.parametrize("chunks,zctas", [(2, None), (4, 1), (7, 2)])
+def test_fused3d_chunked_pipeline_on_one_gpu(monkeypatch, chunks, zctas):
+    # the slab pipeline's chunked launch sequence (kr chunks, comm-stream events) with the exchange a no-op, and the
+    # persistent grid-striding z-column kernel (zctas CTAs per SM) the P2P pipeline uses: same results
     monkeypatch.setenv("PTF_F3_CHUNKS", str(chunks))
+    if zctas is not None:
+        monkeypatch.setenv("PTF_F3_ZCTAS", str(zctas))
     n, L = (64, 128, 64), (2 * np.pi, 4.0, 3.0)
     vel, c0 = _abc(n, L, 0.5)
     for stepper in ("RK4", "FilteredETDRK4", "LSRK54"):
