@@ -116,7 +116,10 @@ class Fused3DEngine final : public Engine {
     // hook (every kernel launch and event of the slab pipeline, with the exchange itself a no-op).
     if (std::getenv("PTF_NO_GRAPH")) ctx.d.use_graph = 0;   // experiment knob: eager launches instead of a captured graph
     const char* ce = std::getenv("PTF_F3_CHUNKS");
-    pipelined = P > 1 || (ce && std::atoi(ce) > 1);
+    // P2P mode runs UNPIPELINED by default: measured on 8 B200 at 1024^3 (profiles/r02_slab3d_scaling.md), the
+    // z-column kernel needs the whole machine's CTAs in flight to keep NVLink busy (33.8 ms/step with full-size launches
+    // against 35.9 / 39.3 ms with 2 / 1 persistent CTAs per SM next to the y kernels).
+    pipelined = (P > 1 && !p2p) || (ce && std::atoi(ce) > 1);
     if (P > 1 && !p2p) ctx.d.use_graph = 0;   // measured: the captured multi-stream NCCL pipeline runs 15 % slower
     if (pipelined) {
       n_chunks = 4;

@@ -317,6 +317,12 @@ void prep3_nt() {
     allow_smem(k_fused_y<N, FAM_RK4, true, true, NT, true, true>, ys);
     allow_smem(k_fused_y<N, FAM_ETD, true, true, NT, true, true>, ys);
     allow_smem(k_fused_y<N, FAM_OTHER, true, true, NT, true, true>, ys);
+    allow_smem(k_fused_y<N, FAM_RK4, true, true, NT, false, true, true>, ys);
+    allow_smem(k_fused_y<N, FAM_ETD, true, true, NT, false, true, true>, ys);
+    allow_smem(k_fused_y<N, FAM_OTHER, true, true, NT, false, true, true>, ys);
+    allow_smem(k_fused_y<N, FAM_RK4, true, true, NT, true, true, true>, ys);
+    allow_smem(k_fused_y<N, FAM_ETD, true, true, NT, true, true, true>, ys);
+    allow_smem(k_fused_y<N, FAM_OTHER, true, true, NT, true, true, true>, ys);
     allow_smem(k_fused_x<N, 0, NT, true>, x3_smem<N, NT>() + g_smem_pad);
     allow_smem(k_yinv3<N, NT>, ys);
     allow_smem(k_yfwd3<N, NT>, ys);
@@ -346,8 +352,20 @@ void launch_z3_nt(bool has_in, int fam, const YArgs& a, cudaStream_t st) {
   if constexpr (NT >= Cfg<N>::T) {
     constexpr int F = NT / Cfg<N>::T;
     dim3 grid((a.cid_end - a.cid0 + F - 1) / F, 1, 1);
-    if (a.grid_cap > 0 && (int)grid.x > a.grid_cap) grid.x = a.grid_cap;
     const size_t sm = y_smem<N, NT>() + g_smem_pad;
+    if (has_in && a.grid_cap > 0 && (int)grid.x > a.grid_cap) {   // small persistent grid (slab pipeline, P2P mode)
+      grid.x = a.grid_cap;
+      if (a.ax.dealias) {
+        if (fam == FAM_RK4) k_fused_y<N, FAM_RK4, true, true, NT, true, true, true><<<grid, NT, sm, st>>>(a);
+        else if (fam == FAM_ETD) k_fused_y<N, FAM_ETD, true, true, NT, true, true, true><<<grid, NT, sm, st>>>(a);
+        else k_fused_y<N, FAM_OTHER, true, true, NT, true, true, true><<<grid, NT, sm, st>>>(a);
+      } else {
+        if (fam == FAM_RK4) k_fused_y<N, FAM_RK4, true, true, NT, false, true, true><<<grid, NT, sm, st>>>(a);
+        else if (fam == FAM_ETD) k_fused_y<N, FAM_ETD, true, true, NT, false, true, true><<<grid, NT, sm, st>>>(a);
+        else k_fused_y<N, FAM_OTHER, true, true, NT, false, true, true><<<grid, NT, sm, st>>>(a);
+      }
+      return;
+    }
     if (a.ax.dealias) {
       if (!has_in) k_fused_y<N, FAM_RK4, false, true, NT, true, true><<<grid, NT, sm, st>>>(a);
       else if (fam == FAM_RK4) k_fused_y<N, FAM_RK4, true, true, NT, true, true><<<grid, NT, sm, st>>>(a);

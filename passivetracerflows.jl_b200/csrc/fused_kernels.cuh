@@ -435,7 +435,10 @@ __device__ __forceinline__ void fused_y_column(const YArgs& a, const int cid_raw
   }
 }
 
-template <int NY, int FAM, bool HAS_IN, bool HAS_OUT, int NT, bool DM = false, bool D3 = false>
+// PERSIST (3-D only) = grid-stride over the columns of the launch: the slab pipeline launches a SMALL persistent grid, so
+//      that this (then NVLink-bound) kernel leaves most CTA slots of every SM to the HBM-bound kernels running next to
+//      it on the main stream.  Kept out of the default kernels: the loop costs them registers (spills).
+template <int NY, int FAM, bool HAS_IN, bool HAS_OUT, int NT, bool DM = false, bool D3 = false, bool PERSIST = false>
 __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
   constexpr int T = Cfg<NY>::T, F = NT / T, PADN = Cfg<NY>::PADN;
   constexpr int TCOLS = NT > 128 ? 256 : 128;
@@ -458,10 +461,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
     t_w = t_nh + 64;
   }
   const int grp = threadIdx.x / T, t = threadIdx.x % T;
-  if (D3) {
-    // 3-D: grid-stride over the columns of this launch.  With a full-size grid every CTA takes one group of columns;
-    // the slab pipeline launches a SMALL persistent grid instead, so that this NVLink-bound kernel leaves most CTA
-    // slots of every SM to the HBM-bound kernels running next to it on the main stream.
+  if (D3 && PERSIST) {
     for (int base = blockIdx.x * F + a.cid0; base < a.cid_end; base += gridDim.x * F) {
       fused_y_column<NY, FAM, HAS_IN, HAS_OUT, NT, DM, D3>(a, base + grp, grp, t, smem, t_nh, t_w);
       if (USE_TMEM) asm volatile("tcgen05.fence::before_thread_sync;");
@@ -469,7 +469,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_y(YArgs a) {
       if (USE_TMEM) asm volatile("tcgen05.fence::after_thread_sync;");
     }
   } else {
-    fused_y_column<NY, FAM, HAS_IN, HAS_OUT, NT, DM, D3>(a, blockIdx.x * F + grp, grp, t, smem, t_nh, t_w);
+    fused_y_column<NY, FAM, HAS_IN, HAS_OUT, NT, DM, D3>(a, blockIdx.x * F + grp + (D3 ? a.cid0 : 0), grp, t, smem, t_nh,
+                                                         t_w);
   }
   if (USE_TMEM) tmem::free_cta<TCOLS>(tbase);
 }
