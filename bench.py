@@ -364,6 +364,54 @@ def run_slab3d(args, rank, world, local_rank, P, dist, barrier, max_over_ranks):
         print(json.dumps(line), flush=True)
 
 
+def run_ensemble(args, rank, world, local_rank, P, dist, barrier, max_over_ranks):
+    """BASELINE configs[4]: an ensemble of `--members` independent 2-D tracers (1024^2 each, own Gaussian centre, shared
+    cellular velocity) sharded over the GPUs by member (PTF_DECOMP_BATCH): no data-path collective.  Strong scaling."""
+    from tests.mgpu_batch_check import member_c0
+    n, B = args.nens, args.members
+    assert B % world == 0, "members must be divisible by the number of GPUs"
+    kappa = 0.1
+    dt = 0.5 * 2.785 / (kappa * 2 * (n / 2) ** 2)
+    flow = P.TwoDAdvectingFlow(u=lambda x, y: 0.2 * np.cos(x) * np.sin(y), v=lambda x, y: -0.2 * np.sin(x) * np.cos(y),
+                               steadyflow=True)
+    dev = P.parallel.init_b200("batch", device=local_rank) if world > 1 else P.B200(device=local_rank)
+    prob = P.Problem(dev, flow, nx=n, kappa=kappa, dt=dt, stepper=args.stepper, nbatch=B)
+    X, Y = P.gridpoints(prob.grid)
+    mine = range(prob.batch_offset, prob.batch_offset + prob.local_nbatch)
+    prob.set_c(np.stack([member_c0(X, Y, b, B) for b in mine]))
+    for _ in range(args.warmup):
+        prob.stepforward(1)
+    own0, lib0 = prob.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_ms = prob.step_timed(args.steps)
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join()
+    own1, lib1 = prob.launch_count()
+    dev_ms = max_over_ranks(dev_ms)
+    npts = n * n * B
+    step_ms = dev_ms / args.steps
+    d = prob.diagnostics()
+    peak, _ = peaks()
+    balg = b_alg(2, args.stepper)
+    if rank == 0:
+        line = {"metric": METRIC, "value": npts * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"ensemble_{B}x{n}^2_{args.stepper}_cellular_flow (BASELINE configs[4]), "
+                                       f"{B // world} members per GPU", "n": n, "members": B, "stepper": args.stepper,
+                           "dt": dt, "engine": prob.engine, "decomposition": "members sharded over ranks, no collective",
+                           "state_finite": bool(np.isfinite(d["max_abs_sol"])), "l2": "fields larger than L2 in total"},
+                "gpu_launches": own1 - own0, "library_calls": lib1 - lib0,
+                "step_roofline": {"b_alg_bytes_per_point_step": balg, "achieved": balg * npts / (step_ms * 1e-3) / 1e9,
+                                  "peak": peak * world, "unit": "GB/s",
+                                  "frac": balg * npts / (step_ms * 1e-3) / 1e9 / (peak * world)},
+                "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+
+
 def run_slab2d(args, rank, world, local_rank, P, dist, barrier, max_over_ranks):
     """One large 2-D cellular-flow problem (BASELINE configs[1] scaled up) slab-decomposed over the GPUs: physical rows
     sharded, spectral kr-columns sharded, one NCCL all-to-all per transform.  Strong scaling."""
@@ -426,7 +474,9 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "cufft", "fused"])
     ap.add_argument("--stepper", default="RK4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cellular2d", choices=["cellular2d", "slab3d", "slab2d"],
+    ap.add_argument("--members", type=int, default=256, help="ensemble workload: number of members (configs[4]: 256)")
+    ap.add_argument("--nens", type=int, default=1024, help="ensemble workload: grid size of each member")
+    ap.add_argument("--workload", default="cellular2d", choices=["cellular2d", "slab3d", "slab2d", "ensemble"],
                     help="cellular2d: BASELINE configs[1], one problem per GPU (default, the graded line); "
                          "slab3d: BASELINE configs[3], ONE n^3 problem slab-decomposed over all GPUs (strong scaling)")
     ap.add_argument("--n3", type=int, default=512, help="grid size of the slab3d workload (n^3)")
@@ -478,6 +528,11 @@ def main():
 
     if args.workload == "slab2d":
         run_slab2d(args, rank, world, local_rank, P, dist, barrier, max_over_ranks)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    if args.workload == "ensemble":
+        run_ensemble(args, rank, world, local_rank, P, dist, barrier, max_over_ranks)
         if dist is not None:
             dist.destroy_process_group()
         return

@@ -147,6 +147,34 @@ def test_fused_config3_layered_512():
     _compare(kw, c0, [1, 4], layered_vel=(u, v, np.array([1.0, 0.0])))
 
 
+def test_fused_config3_layered_512_1000_steps():
+    # the north star's long-run gate (<= 1e-10 after 1000 steps) on BASELINE configs[2] at full size: 2 layers x 512^2,
+    # FilteredRK4, kappa = 0.002, dt = 2.5e-3, frozen flow snapshot + U = [1, 0]   (~70 s of CPU oracle time)
+    n, L, B = (512, 512), (2 * np.pi, 2 * np.pi), 2
+    rng = np.random.default_rng(1234)
+    x, y = _pts(n, L)
+    psi_h = np.zeros((B, n[1], n[0] // 2 + 1), dtype=complex)
+    psi_h[:, :12, :12] = rng.standard_normal((B, 12, 12)) + 1j * rng.standard_normal((B, 12, 12))
+    kx = np.arange(n[0] // 2 + 1)
+    ky = np.where(np.arange(n[1]) < n[1] // 2, np.arange(n[1]), np.arange(n[1]) - n[1])
+    u = np.fft.irfft2(-1j * ky[None, :, None] * psi_h, s=(n[1], n[0]))
+    v = np.fft.irfft2(1j * kx[None, None, :] * psi_h, s=(n[1], n[0]))
+    rms = np.sqrt(np.mean(u ** 2 + v ** 2))
+    u, v = np.ascontiguousarray(u / rms), np.ascontiguousarray(v / rms)
+    c0 = 10 * np.exp(-(x ** 2 + y ** 2) / (2 * 0.15 ** 2))
+    kw = dict(n=n, L=L, kappa=(0.002, 0.002), dt=2.5e-3, stepper="FilteredRK4", velocity="layered", steady=True,
+              nbatch=B)
+    o = OracleProblem(**kw)
+    g = _fused(kw)
+    for p in (o, g):
+        p.set_layered_velocity(u, v, np.array([1.0, 0.0]))
+        p.set_c(c0)
+    o.stepforward(1000)
+    g.stepforward(1000)
+    e = rel_l2(o.updatevars(), g.updatevars())
+    assert e <= TOL_1000, f"configs[2] after 1000 steps: {e:.3e}"
+
+
 def test_fused_time_varying_callback():
     n, L = (256, 256), (2 * np.pi, 2 * np.pi)
     x, y = _pts(n, L)

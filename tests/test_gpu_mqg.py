@@ -178,6 +178,39 @@ def test_coupled_tracer_matches_oracle(engine, n):
     g.close()
 
 
+def test_coupled_loop_per_step_parity_over_a_long_trajectory():
+    """the flow is chaotic, so parity of the coupled loop is a PER-STEP statement.  Over 300 iterations of
+    the example's loop (examples/turbulent_advection-diffusion.jl:149-151) the device is re-synchronised to the oracle's
+    flow state every 10 iterations and must reproduce the next 10 coupled iterations (flow and tracer) to <= 1e-12 per
+    step; the TRACER, which is linear in c and never re-synchronised, must still agree after all 300."""
+    n, kappa, dt = 128, 0.002, 2.5e-3
+    o, g = _pair(n=n, stepper="FilteredRK4", dt=dt, amp=0.5)
+    ad = P().Problem(g, kappa=kappa, stepper="FilteredRK4")
+    o.updatevars()
+    ot = OracleProblem(n=(n, n), L=(2 * np.pi,) * 2, kappa=(kappa, kappa), dt=dt, stepper="FilteredRK4",
+                       velocity="layered", steady=True, nbatch=2)
+    c0 = _tracer_c0(n)
+    ot.set_c(c0)
+    ad.set_c(c0)
+    worst_flow = 0.0
+    for block in range(30):
+        g.set_sol(o.sol)                 # same flow state on both sides at the start of the block
+        g.updatevars()
+        for i in range(10):
+            ot.set_layered_velocity(o.u, o.v, o.params.U)
+            ot.stepforward(1)
+            o.stepforward(1)
+            o.updatevars()
+        P().MultiLayerQG.step_coupled(ad, 10)
+        e = rel_l2(o.sol, g.sol)
+        worst_flow = max(worst_flow, e)
+        assert e < 10 * TOL_STEP, f"block {block}: flow after 10 coupled iterations {e:.3e}"
+    e_c = rel_l2(ot.updatevars(), ad.updatevars())
+    assert e_c < TOL_20, f"tracer after 300 coupled iterations: {e_c:.3e} (worst flow block {worst_flow:.2e})"
+    ad.close()
+    g.close()
+
+
 def test_two_tracers_coupled_to_one_flow_are_ordered_across_streams():
     """The flow adopts the stream of the tracer that coupled last; stepping the OTHER tracer through step_coupled runs
     its kernels on a different stream than the flow's and must be ordered with events (data race)."""

@@ -141,3 +141,97 @@ def test_slab2d_transpose_scheme_world2(n):
         assert p.exitcode == 0
     for rank, e_f, e_i, e_pad in res:
         assert e_f < 1e-13 and e_i < 1e-13 and e_pad == 0.0, (rank, e_f, e_i, e_pad)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Fused 3-D engine, slab-decomposed (csrc/engine_fused3d.cu, fused3d_kernels.cuh): the producing kernels write the blocks
+# of the exchange directly in the receiver's layout — P^xy as [p][kr][zl/8][ll][zl%8], A / C as [p][kr][ll][zl] — so the
+# all-to-all moves contiguous blocks and nothing is packed or unpacked.  Same index formulas as the kernels, NumPy FFTs
+# standing in for the in-kernel transforms.
+# ---------------------------------------------------------------------------------------------------------------------
+def _worker_fused3d(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nx, ny, nz = n
+    nkr = nx // 2 + 1
+    nzl, nyl = nz // world, ny // world
+    zoff, yoff = rank * nzl, rank * nyl
+    rng = np.random.default_rng(7)
+    c = rng.standard_normal((nz, ny, nx))
+    ref = np.fft.rfftn(c)                                                   # [m][l][kr]
+    # forward: x row kernel + y-forward kernel give FFT_y FFT_x of the local planes ...
+    T1 = np.fft.fft(np.fft.rfft(c[zoff:zoff + nzl], axis=2), axis=1)        # [zl][l][kr]
+    # ... which k_yfwd3 stores as PXY[p][kr][zl/8][ll][zl%8] (p = l / nyl)
+    send = np.empty((world, nkr, nzl // 8, nyl, 8), dtype=np.complex128)
+    for zl in range(nzl):
+        for l in range(ny):
+            send[l // nyl, :, zl // 8, l % nyl, zl % 8] = T1[zl, l, :]
+    recv = _a2a(send)                                                       # [r][kr][zl/8][ll][zl%8], r = source rank
+    # the z-column kernel gathers column (kr, ll): element z lives in block r = z / nzl
+    spec = np.empty((nkr, nyl, nz), dtype=np.complex128)                    # state layout [kr][ll][z]
+    for z in range(nz):
+        r, zl = z // nzl, z % nzl
+        spec[:, :, z] = recv[r, :, zl // 8, :, zl % 8]
+    spec = np.fft.fft(spec, axis=2)
+    e_f = np.abs(spec - ref[:, yoff:yoff + nyl, :].transpose(2, 1, 0)).max() / np.abs(ref).max()
+    # inverse: the z-column kernel stores A = IFFT_z(s) as ZA[p][kr][ll][zl] (p = z / nzl)
+    A = np.fft.ifft(spec, axis=2) * nz
+    sendA = np.empty((world, nkr, nyl, nzl), dtype=np.complex128)
+    for z in range(nz):
+        sendA[z // nzl, :, :, z % nzl] = A[:, :, z]
+    recvA = _a2a(sendA)                                                     # [r][kr][ll][zl], r = l / nyl
+    # k_yinv3 reads column (zl, kr): element l lives in block r = l / nyl
+    Yc = np.empty((nzl, nkr, ny), dtype=np.complex128)                      # [zl][kr][l]
+    for l in range(ny):
+        Yc[:, :, l] = recvA[l // nyl, :, l % nyl, :].T
+    Yp = np.fft.ifft(Yc, axis=2) * ny                                       # [zl][kr][y]
+    back = np.fft.irfft(Yp.transpose(0, 2, 1), n=nx, axis=2) / (ny * nz)    # x row kernel: c2r along x
+    e_i = np.abs(back - c[zoff:zoff + nzl]).max()
+    q.put((rank, float(e_f), float(e_i)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [(8, 4, 16), (6, 8, 32)])
+def test_fused3d_slab_layouts_world2(n):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_fused3d, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, e_f, e_i in res:
+        assert e_f < 1e-13 and e_i < 1e-13, (rank, e_f, e_i)
+
+
+@pytest.mark.parametrize("P", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("ny,nz", [(64, 64), (128, 256), (1024, 128)])
+def test_fused3d_flattened_strides_match_the_block_layouts(P, ny, nz):
+    """engine_fused3d.cu y3args(): element l = t + T*e of a y column is addressed as base(t) + e*s_e + (e >> esh)*s_r.
+    Must equal the block layouts [r][kr][ll][zl] (k_yinv3 input) and [p][kr][zl/8][ll][zl%8] (k_yfwd3 output)."""
+    nkx = 5
+    nyl, nzl = ny // P, nz // P
+    if nzl < 8:
+        pytest.skip("each rank needs at least 8 planes")
+    T = ny // 16
+    blk = nkx * nyl * nzl
+    esh = (16 // P).bit_length() - 1
+    in_se, in_sr = T * nzl, blk - nyl * nzl
+    out_se, out_sr = T * 8, blk - nyl * 8
+    rng = np.random.default_rng(P + ny)
+    for _ in range(20):
+        kr, t, e = int(rng.integers(nkx)), int(rng.integers(T)), int(rng.integers(16))
+        zl = 2 * int(rng.integers(nzl // 2))
+        l = t + T * e
+        r, ll = l // nyl, l % nyl
+        want_in = ((r * nkx + kr) * nyl + ll) * nzl + zl
+        got_in = (kr * nyl + t) * nzl + zl + e * in_se + (e >> esh) * in_sr
+        assert want_in == got_in
+        want_out = (((r * nkx + kr) * (nzl // 8) + zl // 8) * nyl + ll) * 8 + zl % 8
+        got_out = ((kr * (nzl // 8) + zl // 8) * nyl + t) * 8 + zl % 8 + e * out_se + (e >> esh) * out_sr
+        assert want_out == got_out
