@@ -180,11 +180,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("PTF_LIB_PATH") or LIB_PATH     # PTF_LIB_PATH: developer knob (A/B builds, build.py --variant)
+    if not os.path.exists(path):
         raise ImportError(f"{LIB_PATH} is missing: build it with `python passivetracerflows.jl_b200/build.py` "
                           "(__graft_entry__.build()).  This package has no CPU / PyTorch fallback.")
     _preload_nccl()
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL if hasattr(C, "RTLD_GLOBAL") else 0)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL if hasattr(C, "RTLD_GLOBAL") else 0)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -32,23 +32,33 @@ def needs_build():
     return _newest(deps) > os.path.getmtime(LIB)
 
 
-def build(force=False, verbose=False, with_nccl=True):
+def build(force=False, verbose=False, with_nccl=True, variant=None, defines=()):
+    """variant / defines: developer knob for A/B experiments — builds libptf_b200_<variant>.so with extra -D flags into
+    its own object directory; load it with PTF_LIB_PATH=<that file> (see _capi.load)."""
+    global LIB
+    if variant:
+        return _build(True, verbose, with_nccl, os.path.join(HERE, f"libptf_b200_{variant}.so"),
+                      os.path.join(HERE, f"build_{variant}"), [f"-D{d}" for d in defines])
     if not force and not needs_build():
         return LIB
+    return _build(force, verbose, with_nccl, LIB, os.path.join(HERE, "build"), [])
+
+
+def _build(force, verbose, with_nccl, LIB, BUILD, extra_defs):
     nvcc = _nvcc()
     objs = []
     common = [nvcc, "-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
-              "-I", os.path.join(HERE, "..", "include")]
+              "-I", os.path.join(HERE, "..", "include"), *extra_defs]
     if verbose:
         common += ["-Xptxas", "-v"]
     if with_nccl:
         common += ["-DPTF_WITH_NCCL"]
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(BUILD, exist_ok=True)
     procs = []
     jobs = [(s, s.replace(".cu", ".o"), []) for s in SOURCES]
     jobs += [("fused_inst.cu", f"fused_inst_{n}.o", [f"-DPTF_INST_N={n}"]) for n in FUSED_SIZES]
     for s, oname, extra in jobs:
-        o = os.path.join(HERE, "build", oname)
+        o = os.path.join(BUILD, oname)
         objs.append(o)
         src = os.path.join(CSRC, s)
         if (not force) and os.path.exists(o) and os.path.getmtime(o) > _newest(
@@ -74,4 +84,8 @@ def build(force=False, verbose=False, with_nccl=True):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:   # python build.py --variant nb8 PTF_RK4_NB=8
+        i = sys.argv.index("--variant")
+        print(build(variant=sys.argv[i + 1], defines=[a for a in sys.argv[i + 2:] if "=" in a or a.isidentifier()]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -74,6 +74,7 @@ class FusedEngine final : public Engine {
       tune_stagger_y = env_int("PTF_STAGGER_Y", 25000);
       PTF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx.device));
       tune_ablate_y = env_int("PTF_ABLATE_Y", 0);
+      tune_x_direct = env_int("PTF_X_DIRECT", 1);   // measured: row kernel 0.229 -> 0.210 ms at 4096^2 (profiles/r02_*)
     }
     PTF_DISPATCH_N(ny, fused_prep);
     if (nx != ny) PTF_DISPATCH_N(nx, fused_prep);
@@ -256,6 +257,7 @@ class FusedEngine final : public Engine {
       a.stagger = ctas >= 4L * a.first_wave ? tune_stagger_x : 0;
     }
     int vmode = (vs.va.kind == PTF_FLOW_SEPARABLE) ? 2 : (vs.va.ushift ? 1 : 0);
+    if (vmode != 2 && tune_x_direct) vmode = 3;
     if (vmode != 2 && (!vs.va.arr[0] || !vs.va.arr[1]))
       throw Error(PTF_EINVAL, "velocity fields have not been set (ptf_set_velocity / callback)");
     PTF_DISPATCH_N(nx, fused_launch_x, vmode, &a, nb, ctx.stream, n_sm);
@@ -409,7 +411,7 @@ class FusedEngine final : public Engine {
   cufftHandle plan_fwd = 0, plan_inv = 0;
   bool ab_valid = false;
   int tune_ablate_x = 0, tune_ablate_y = 0, tune_stagger_x = 0, tune_stagger_y = 0, n_sm = 148;
-  int tune_pf_state = 0, tune_pf_vel = 0, tune_pf_ahead_y = 0, tune_pf_ahead_x = 0;
+  int tune_pf_state = 0, tune_pf_vel = 0, tune_pf_ahead_y = 0, tune_pf_ahead_x = 0, tune_x_direct = 0;
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
   int64_t per_step_own = 0;
 };

@@ -436,7 +436,7 @@ class Fused3DEngine final : public Engine {
     a.first_wave = 0;
     a.nzg = nz;
     a.zoff = (int)g.zoff;
-    int vmode = 0;
+    int vmode = std::getenv("PTF_X_DIRECT") && std::atoi(std::getenv("PTF_X_DIRECT")) ? 3 : 0;
     if (vs.va.kind == PTF_FLOW_SEPARABLE) {
       if (!sepv[0].p) throw Error(PTF_EINVAL, "separable velocity tables have not been set");
       for (int c = 0; c < 3; ++c) a.va.arr[c] = sepv[c].p;

@@ -205,13 +205,25 @@ __device__ __forceinline__ void last_pass(double2 (&v)[16], int t, const double2
   }
 }
 
-// One transform by T cooperating threads of a CTA; all threads of the CTA must call it (CTA-wide barriers).
+// Barrier among the T threads of ONE transform group (group `grp` of a CTA of NT threads).  Groups of a CTA are
+// independent transforms: with CTA-wide barriers they would run in lock-step (every exchange waits for the slowest
+// group's memory phase); named barriers / warp barriers let each group proceed on its own.
+template <int T, int NT>
+__device__ __forceinline__ void group_sync(int grp) {
+  if (NT == 0 || T >= NT) __syncthreads();
+  else if (T >= 32) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(T) : "memory");
+  else __syncwarp();   // T < 32 divides the warp: a group never spans two warps
+}
+
+// One transform by T cooperating threads of a CTA; all threads of the CTA must call it (CTA-wide barriers, or with
+// NT > 0 barriers among the T threads of group `grp` only).
 // `sm` points at this transform's padded buffer; it may be reused by the caller after the call returns AND a barrier.
 // OPAQUE_TW: hide the twiddle-table pointers from the optimiser for this call.  A kernel that runs several transforms
 // of the same length back to back otherwise gets their (identical) twiddle loads merged and kept live across the
 // transforms in between: up to 48 registers, i.e. spills at 128 registers per thread.
-template <int N, int DIR, bool OPAQUE_TW = false>
-__device__ __forceinline__ void fft_cta(double2 (&v)[16], double2* __restrict__ sm, int t, const Twiddles& tw_in) {
+template <int N, int DIR, bool OPAQUE_TW = false, int NT = 0>
+__device__ __forceinline__ void fft_cta(double2 (&v)[16], double2* __restrict__ sm, int t, const Twiddles& tw_in,
+                                        int grp = 0) {
   constexpr int T = Cfg<N>::T, R3 = Cfg<N>::R3;
   Twiddles tw = tw_in;
   if (OPAQUE_TW) {
@@ -220,10 +232,10 @@ __device__ __forceinline__ void fft_cta(double2 (&v)[16], double2* __restrict__ 
   }
   // ---- pass 1: radix 16, Ns = 1, no twiddles ----
   dft16<DIR>(v);
-  __syncthreads();  // buffer free (previous readers done)
+  group_sync<T, NT>(grp);  // buffer free (previous readers done)
 #pragma unroll
   for (int r = 0; r < 16; ++r) sm[pad_idx(16 * t + r)] = v[sl16(r)];
-  __syncthreads();
+  group_sync<T, NT>(grp);
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
   if (Cfg<N>::TWO_PASS) {  // N = 64, 128: last pass radix N/16 over the 16-point sub-transforms
@@ -240,13 +252,13 @@ __device__ __forceinline__ void fft_cta(double2 (&v)[16], double2* __restrict__ 
   }
   dft16<DIR>(v);
   if (R3 == 1) return;
-  __syncthreads();
+  group_sync<T, NT>(grp);
   {
     const int base = 16 * (t - k2) + k2;
 #pragma unroll
     for (int r = 0; r < 16; ++r) sm[pad_idx(base + 16 * r)] = v[sl16(r)];
   }
-  __syncthreads();
+  group_sync<T, NT>(grp);
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
   // ---- pass 3: radix R3, Ns = 256 ----

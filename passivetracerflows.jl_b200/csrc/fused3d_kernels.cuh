@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_yinv3(Y3Args a) {
       }
       tmem::wait_st();
     }
-    fft::fft_cta<NY, +1>(v, sm, t, a.tw);
+    fft::fft_cta<NY, +1, false, NT>(v, sm, t, a.tw, grp);
     double2* dst = (it == 0 || it == 2) ? a.YA : ((it == 1 || it == 3) ? a.YB : a.YC);
     const int zq = zl + ((it == 2 || it == 3 || it == 5) ? 1 : 0);
     if (active) {
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_yfwd3(Y3Args a) {
 #pragma unroll
       for (int e = 0; e < 16; ++e) v[e] = __ldcg(Pt + (e >> 1) * se + 4 * (e & 1));
     }
-    fft::fft_cta<NY, -1>(v, sm, t, a.tw);
+    fft::fft_cta<NY, -1, false, NT>(v, sm, t, a.tw, grp);
     if (q == 0) {
 #pragma unroll
       for (int e = 0; e < 16; ++e) tmem::st1(t_r + 4 * e, v[out_slot<NY>(e)]);
@@ -324,6 +324,7 @@ void prep3_nt() {
     allow_smem(k_fused_y<N, FAM_ETD, true, true, NT, true, true, true>, ys);
     allow_smem(k_fused_y<N, FAM_OTHER, true, true, NT, true, true, true>, ys);
     allow_smem(k_fused_x<N, 0, NT, true>, x3_smem<N, NT>() + g_smem_pad);
+    allow_smem(k_fused_x<N, 3, NT, true>, x3_smem<N, NT>() + g_smem_pad);
     allow_smem(k_yinv3<N, NT>, ys);
     allow_smem(k_yfwd3<N, NT>, ys);
   }
@@ -391,8 +392,9 @@ void launch_x3_nt(int vmode, const XArgs& a, int nplanes, cudaStream_t st) {
     constexpr int F = NT / Cfg<N>::T;
     dim3 grid((a.ny / 2 + F - 1) / F, nplanes, 1);
     const size_t sm = x3_smem<N, NT>() + g_smem_pad;
-    (void)vmode;   // separable flows are written out once per step (k_sep_fill): the row kernel always reads arrays
-    k_fused_x<N, 0, NT, true><<<grid, NT, sm, st>>>(a);
+    // separable flows are written out once per step (k_sep_fill): the row kernel always reads arrays
+    if (vmode == 3) k_fused_x<N, 3, NT, true><<<grid, NT, sm, st>>>(a);
+    else k_fused_x<N, 0, NT, true><<<grid, NT, sm, st>>>(a);
   }
 }
 template <int N>

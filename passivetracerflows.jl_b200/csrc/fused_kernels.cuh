@@ -108,7 +108,10 @@ struct ColId {
 template <int NY, int MODE, bool DM, bool FILT, bool D3>
 __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_t t_w, size_t col, int t,
                                           const ColId& c, bool active, const double (&fl)[16]) {
-  constexpr int T = Cfg<NY>::T, NB = 4;
+#ifndef PTF_RK4_NB
+#define PTF_RK4_NB 4
+#endif
+  constexpr int T = Cfg<NY>::T, NB = PTF_RK4_NB;
   const double dt = a.C.dt;
   const double kx = c.kx;
 #pragma unroll
@@ -330,7 +333,7 @@ __device__ __forceinline__ void fused_y_column(const YArgs& a, const int cid_raw
           for (int e = 0; e < 16; ++e) prefetch_l2(a.pf_r[q] + ccol + t + T * e);
         }
     }
-    fft::fft_cta<NY, -1>(v, sm, t, a.tw);
+    fft::fft_cta<NY, -1, false, NT>(v, sm, t, a.tw, grp);
     if (!D3 && a.pf_ahead > 0) {  // next wave's gather: one 32-byte sector per (y, kr') pair
       const int kr2 = cid_raw + a.pf_ahead * F;
       if (kr2 < a.nkr) {
@@ -401,7 +404,7 @@ __device__ __forceinline__ void fused_y_column(const YArgs& a, const int cid_raw
     if (D3) return dst3d[l >> a.zsh] + ((size_t)cid << a.zsh) + (l & (a.nzl - 1));
     return base2d + col + l;
   };
-  fft::fft_cta<NY, +1>(w, sm, t, a.tw);
+  fft::fft_cta<NY, +1, false, NT>(w, sm, t, a.tw, grp);
   if (active) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) __stcg(out_ptr(a.A, a.Adst, t + T * e), w[out_slot<NY>(e)]);
@@ -428,7 +431,7 @@ __device__ __forceinline__ void fused_y_column(const YArgs& a, const int cid_raw
       w[e] = make_double2(-ky * s.y, ky * s.x);
     }
   }
-  fft::fft_cta<NY, +1>(w, sm, t, a.tw);
+  fft::fft_cta<NY, +1, false, NT>(w, sm, t, a.tw, grp);
   if (active) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) __stcg(out_ptr(a.Bf, a.Cdst, t + T * e), w[out_slot<NY>(e)]);
@@ -539,7 +542,23 @@ template <int NX, int VMODE, bool D3W = false, bool D3 = false>
 __device__ __forceinline__ void x_request_uv(const XArgs& a, size_t voff, int q, int t, uint32_t t_uv) {
   constexpr int T = Cfg<NX>::T;
   constexpr int UB = 8;  // velocity request batch
-  if (VMODE != 2) {
+  if (VMODE == 3) {
+    // direct mode: only pull the rows into L2 now (one request per 32-byte sector); x_product loads them from there
+    // after the transform — no TMEM parking, and this warp does not wait here for HBM
+    if ((t & 3) == 0) {
+      const size_t i0 = voff + (size_t)q * NX + t;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        if (D3W) {
+          prefetch_l2(a.va.arr[2] + i0 + T * e);
+          prefetch_l2(a.va.arr[2] + i0 + NX + T * e);
+        } else {
+          prefetch_l2(a.va.arr[0] + i0 + T * e);
+          prefetch_l2(a.va.arr[1] + i0 + T * e);
+        }
+      }
+    }
+  } else if (VMODE != 2) {
     // 3-D: one opaque base per field and compile-time offsets T*e, so that no per-element address outlives this call
     // (hoisted out of the row loop they would cost 64 registers)
     const size_t i0 = D3 ? fft::opaque(voff + (size_t)q * NX + t) : 0;
@@ -566,11 +585,19 @@ __device__ __forceinline__ void x_product(const XArgs& a, const double2 (&v)[16]
                                           double* __restrict__ ps, int t, uint32_t t_uv, int b, int pair) {
   constexpr int T = Cfg<NX>::T;
   const int row = 2 * pair + Q;
-  constexpr int PB = 4;  // velocity fetch batch
+  constexpr int PB = VMODE == 3 ? 8 : 4;  // velocity fetch batch
+  const size_t vi0 = VMODE == 3 ? fft::opaque((D3 ? (size_t)b * a.ny * NX : (size_t)b * a.va.member_stride) +
+                                              (size_t)row * NX + t)
+                                : 0;
 #pragma unroll
   for (int c = 0; c < 16 / PB; ++c) {
     double2 uv[PB];
-    if (VMODE != 2) tmem::ldn<PB>(t_uv + 4 * PB * c, uv);
+    if (VMODE == 3) {
+#pragma unroll
+      for (int j = 0; j < PB; ++j)
+        uv[j] = make_double2(tmem::ldg64(a.va.arr[0] + vi0 + T * (PB * c + j)),
+                             tmem::ldg64(a.va.arr[1] + vi0 + T * (PB * c + j)));
+    } else if (VMODE != 2) tmem::ldn<PB>(t_uv + 4 * PB * c, uv);
 #pragma unroll
     for (int j = 0; j < PB; ++j) {
       const int e = PB * c + j, x = t + T * e;
@@ -596,11 +623,17 @@ template <int NX, int VMODE>
 __device__ __forceinline__ void x_product_z(const XArgs& a, const double2 (&v)[16], double* __restrict__ ps, int t,
                                             uint32_t t_uv, int b, int pair) {
   constexpr int T = Cfg<NX>::T;
-  constexpr int PB = 4;
+  constexpr int PB = VMODE == 3 ? 8 : 4;
+  const size_t vi0 = VMODE == 3 ? fft::opaque((size_t)b * a.ny * NX + (size_t)(2 * pair) * NX + t) : 0;
 #pragma unroll
   for (int c = 0; c < 16 / PB; ++c) {
     double2 ww[PB];
-    if (VMODE != 2) tmem::ldn<PB>(t_uv + 4 * PB * c, ww);
+    if (VMODE == 3) {
+#pragma unroll
+      for (int j = 0; j < PB; ++j)
+        ww[j] = make_double2(tmem::ldg64(a.va.arr[2] + vi0 + T * (PB * c + j)),
+                             tmem::ldg64(a.va.arr[2] + vi0 + NX + T * (PB * c + j)));
+    } else if (VMODE != 2) tmem::ldn<PB>(t_uv + 4 * PB * c, ww);
 #pragma unroll
     for (int j = 0; j < PB; ++j) {
       const int e = PB * c + j, x = t + T * e;
@@ -687,7 +720,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
   for (int q = 0; q < NQ; ++q) {  // deliberately NOT unrolled: one copy of the inverse transform keeps register
                                   // pressure (and the instruction footprint) down
     if (q == 1) {
-      __syncthreads();           // exchange buffer free (row 0's transform readers are done)
+      fft::group_sync<T, NT>(grp);  // exchange buffer free (row 0's transform readers are done)
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
         double2 AB[4];  // (A1, B1) of k-slots 2h, 2h+1
@@ -713,7 +746,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
     }
     if constexpr (D3) {
       if (q == 2) {
-        __syncthreads();         // exchange buffer free (row 1's transform readers are done)
+        fft::group_sync<T, NT>(grp);  // exchange buffer free (row 1's transform readers are done)
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           double2 CC[4];         // (C0, C1) of k-slots 2h, 2h+1
@@ -735,10 +768,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
       x_nyquist<NX>(t, Ab, Bb, ny, q, a.ax.kx, sm);
       x_request_uv<NX, VMODE>(a, voff, q, t, t_uv);  // includes tcgen05.wait::st for the parked inputs as well
     }
-    __syncthreads();
+    fft::group_sync<T, NT>(grp);
 #pragma unroll
     for (int e = 8; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
-    fft::fft_cta<NX, +1>(v, sm, t, a.tw);
+    fft::fft_cta<NX, +1, false, NT>(v, sm, t, a.tw, grp);
     if constexpr (D3) {
       if (q == 0) x_product<NX, VMODE, 0, true>(a, v, v, ps, t, t_uv, b, pair);
       else if (q == 1) x_product<NX, VMODE, 1, true>(a, v, v, ps, t, t_uv, b, pair);
@@ -756,11 +789,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
   }
 
   // ---------------- forward transform of the row pair packed as p_y + i*p_{y+1} ----------------
-  fft::fft_cta<NX, -1>(w, sm, t, a.tw);
-  __syncthreads();
+  fft::fft_cta<NX, -1, false, NT>(w, sm, t, a.tw, grp);
+  fft::group_sync<T, NT>(grp);
 #pragma unroll
   for (int e = 8; e < 16; ++e) sm[pad_idx(t + T * e)] = w[out_slot<NX>(e)];
-  __syncthreads();
+  fft::group_sync<T, NT>(grp);
   // blocked layout [b][y/8][kr][y%8]: rows y0 = 2*pair and y0+1 of one kr are 32 contiguous, 32-byte aligned bytes
   const int y0 = 2 * pair;
   double2* P0 = a.Px + (size_t)b * ny * a.nkr + (size_t)(y0 >> 3) * a.nkr * 8 + (y0 & 7);
@@ -1038,6 +1071,7 @@ void prep_x_nt() {
   if constexpr (NT >= Cfg<NX>::T) {
     allow_smem(k_fused_x<NX, 0, NT>, x_smem<NX, NT>() + g_smem_pad);
     allow_smem(k_fused_x<NX, 2, NT>, x_smem<NX, NT>() + g_smem_pad);
+    allow_smem(k_fused_x<NX, 3, NT>, x_smem<NX, NT>() + g_smem_pad);
   }
 }
 template <int NX>
@@ -1081,6 +1115,7 @@ void launch_x_nt(int vmode, const XArgs& a, int nb, cudaStream_t st) {
     dim3 grid((a.ny / 2) / F, nb, 1);
     size_t sm = x_smem<NX, NT>() + g_smem_pad;
     if (vmode == 2) k_fused_x<NX, 2, NT><<<grid, NT, sm, st>>>(a);
+    else if (vmode == 3) k_fused_x<NX, 3, NT><<<grid, NT, sm, st>>>(a);
     else k_fused_x<NX, 0, NT><<<grid, NT, sm, st>>>(a);
   }
 }
