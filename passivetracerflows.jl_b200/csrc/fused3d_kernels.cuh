@@ -324,7 +324,7 @@ void prep3_nt() {
     allow_smem(k_fused_y<N, FAM_ETD, true, true, NT, true, true, true>, ys);
     allow_smem(k_fused_y<N, FAM_OTHER, true, true, NT, true, true, true>, ys);
     allow_smem(k_fused_x<N, 0, NT, true>, x3_smem<N, NT>() + g_smem_pad);
-    allow_smem(k_fused_x<N, 3, NT, true>, x3_smem<N, NT>() + g_smem_pad);
+    allow_smem(k_fused_x<N, 3, NT, true>, y_smem<N, NT>() + g_smem_pad);   // direct mode: products parked in TMEM
     allow_smem(k_yinv3<N, NT>, ys);
     allow_smem(k_yfwd3<N, NT>, ys);
   }
@@ -393,7 +393,7 @@ void launch_x3_nt(int vmode, const XArgs& a, int nplanes, cudaStream_t st) {
     dim3 grid((a.ny / 2 + F - 1) / F, nplanes, 1);
     const size_t sm = x3_smem<N, NT>() + g_smem_pad;
     // separable flows are written out once per step (k_sep_fill): the row kernel always reads arrays
-    if (vmode == 3) k_fused_x<N, 3, NT, true><<<grid, NT, sm, st>>>(a);
+    if (vmode == 3) k_fused_x<N, 3, NT, true><<<grid, NT, y_smem<N, NT>() + g_smem_pad, st>>>(a);
     else k_fused_x<N, 0, NT, true><<<grid, NT, sm, st>>>(a);
   }
 }

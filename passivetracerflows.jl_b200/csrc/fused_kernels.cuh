@@ -598,6 +598,7 @@ __device__ __forceinline__ void x_product(const XArgs& a, const double2 (&v)[16]
         uv[j] = make_double2(tmem::ldg64(a.va.arr[0] + vi0 + T * (PB * c + j)),
                              tmem::ldg64(a.va.arr[1] + vi0 + T * (PB * c + j)));
     } else if (VMODE != 2) tmem::ldn<PB>(t_uv + 4 * PB * c, uv);
+    double pprev = 0.0;
 #pragma unroll
     for (int j = 0; j < PB; ++j) {
       const int e = PB * c + j, x = t + T * e;
@@ -612,11 +613,15 @@ __device__ __forceinline__ void x_product(const XArgs& a, const double2 (&v)[16]
         if (!D3 && a.va.ushift) u += a.va.ushift[b * a.ny + row];  // layered flows: u + U(y, layer)  (TAD.jl:795)
       }
       const double p = -u * g.x - vv * g.y;
-      if (D3) ps[Q * NX + x] = p;
+      if (D3 && VMODE == 3) {                    // 3-D direct mode: parked in the (free) velocity slot of TMEM, two
+        if (j & 1) tmem::st1(t_uv + 32 * Q + 2 * (e - 1), make_double2(pprev, p));   // points per 4-column entry
+        pprev = p;
+      } else if (D3) ps[Q * NX + x] = p;
       else if (Q == 0) ps[x] = p;                // row 0: parked in shared memory while row 1 runs
       else w[e] = make_double2(ps[x], p);        // row 1: packed with row 0 as p_y + i*p_{y+1} for the forward FFT
     }
   }
+  if (D3 && VMODE == 3) tmem::wait_st();
 }
 // 3-D: v = gz(row 0) + i*gz(row 1);  p_q -= w_q * gz_q  (TAD.jl:781), completed in the shared-memory parking rows
 template <int NX, int VMODE>
@@ -634,6 +639,11 @@ __device__ __forceinline__ void x_product_z(const XArgs& a, const double2 (&v)[1
         ww[j] = make_double2(tmem::ldg64(a.va.arr[2] + vi0 + T * (PB * c + j)),
                              tmem::ldg64(a.va.arr[2] + vi0 + NX + T * (PB * c + j)));
     } else if (VMODE != 2) tmem::ldn<PB>(t_uv + 4 * PB * c, ww);
+    double2 pa[PB / 2], pb[PB / 2];   // direct mode: the parked partial products of rows 0 and 1
+    if (VMODE == 3) {
+      tmem::ldn<PB / 2>(t_uv + 2 * PB * c, pa);
+      tmem::ldn<PB / 2>(t_uv + 32 + 2 * PB * c, pb);
+    }
 #pragma unroll
     for (int j = 0; j < PB; ++j) {
       const int e = PB * c + j, x = t + T * e;
@@ -646,10 +656,28 @@ __device__ __forceinline__ void x_product_z(const XArgs& a, const double2 (&v)[1
         w0 = ww[j].x;
         w1 = ww[j].y;
       }
-      ps[x] = ps[x] - w0 * g.x;
-      ps[NX + x] = ps[NX + x] - w1 * g.y;
+      if (VMODE == 3) {   // finished products replace the partial ones in place
+        if (j & 1) {
+          pa[j / 2].y = pa[j / 2].y - w0 * g.x;
+          pb[j / 2].y = pb[j / 2].y - w1 * g.y;
+        } else {
+          pa[j / 2].x = pa[j / 2].x - w0 * g.x;
+          pb[j / 2].x = pb[j / 2].x - w1 * g.y;
+        }
+      } else {
+        ps[x] = ps[x] - w0 * g.x;
+        ps[NX + x] = ps[NX + x] - w1 * g.y;
+      }
+    }
+    if (VMODE == 3) {
+#pragma unroll
+      for (int k = 0; k < PB / 2; ++k) {
+        tmem::st1(t_uv + 2 * PB * c + 4 * k, pa[k]);
+        tmem::st1(t_uv + 32 + 2 * PB * c + 4 * k, pb[k]);
+      }
     }
   }
+  if (VMODE == 3) tmem::wait_st();
 }
 
 // VMODE 0: velocity arrays; 1: arrays + layered shift U(y,b); 2: separable tables (zero HBM bytes)
@@ -781,7 +809,19 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
     }
   }
   double2 w[16];
-  if constexpr (D3) {            // both rows' finished products come back from shared memory (same thread wrote them)
+  if constexpr (D3 && VMODE == 3) {   // both rows' finished products come back from TMEM, two points per entry
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double2 pa[4], pb[4];
+      tmem::ldn<4>(t_uv + 16 * h, pa);
+      tmem::ldn<4>(t_uv + 32 + 16 * h, pb);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        w[8 * h + 2 * k] = make_double2(pa[k].x, pb[k].x);
+        w[8 * h + 2 * k + 1] = make_double2(pa[k].y, pb[k].y);
+      }
+    }
+  } else if constexpr (D3) {     // both rows' finished products come back from shared memory (same thread wrote them)
 #pragma unroll
     for (int e = 0; e < 16; ++e) w[e] = make_double2(ps[t + T * e], ps[NX + t + T * e]);
   } else {
