@@ -83,14 +83,16 @@ enum {
 enum {
   PTF_ENGINE_AUTO = 0,  /* fused hand-written FFT pipeline when the grid qualifies, else the cuFFT pipeline */
   PTF_ENGINE_CUFFT = 1, /* cuFFT D2Z/Z2D + fused pointwise kernels: any even grid size */
-  PTF_ENGINE_FUSED = 2  /* hand-written shared-memory FFTs with all pointwise work fused into their I/O */
+  PTF_ENGINE_FUSED = 2  /* hand-written shared-memory FFTs with all pointwise work fused into their I/O: 2-D grids
+                           64..4096 per axis, 3-D grids 64..1024 per axis (also slab-decomposed), 1-D <= 2048 */
 };
 
 /* how a multi-rank job is partitioned (one process per GPU; rank/nranks below) */
 enum {
   PTF_DECOMP_NONE = 0,  /* single GPU, or independent replicas */
   PTF_DECOMP_BATCH = 1, /* ensemble members / layers sharded over ranks, no communication */
-  PTF_DECOMP_SLAB = 2   /* last physical axis sharded; NCCL all-to-all transpose inside each transform */
+  PTF_DECOMP_SLAB = 2   /* last physical axis sharded; one all-to-all per transform: peer-to-peer over NVLink fused into
+                           the z-column kernel (fused 3-D engine, CUDA IPC) or NCCL send/recv (cuFFT / 2-D slab engines) */
 };
 
 typedef struct ptf_handle ptf_handle;
