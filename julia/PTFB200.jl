@@ -51,6 +51,7 @@ mutable struct Prob
   h::Ptr{Cvoid}; sol::Array{ComplexF64}; clock::Clock; vars::Vars
   n::NTuple{3,Int}; L::NTuple{3,Float64}; ndim::Int
   velocity                                   # keeps the @cfunction closure alive
+  nbatch::Int                                # layers of an MQG-coupled problem (1 otherwise)
 end
 
 gridpoints1(n, L) = range(-L/2, step=L/n, length=n)
@@ -91,14 +92,15 @@ function Problem(dev::B200, flow; nx=128, Lx=2π, ny=nx, Ly=Lx, nz=nx, Lz=Lx, κ
     check(ccall((:ptf_set_velocity_callback, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), h[], keep, C_NULL), h[])
   end
   p = Prob(h[], zeros(ComplexF64, sdims), Clock(dt, 0.0, 0), Vars(zeros(dims), zeros(ComplexF64, sdims)),
-           (nx, ny, nz), (Lx, Ly, Lz), ndim, keep)
+           (nx, ny, nz), (Lx, Ly, Lz), ndim, keep, 1)
   finalizer(q -> ccall((:ptf_destroy, LIB), Int32, (Ptr{Cvoid},), q.h), p)
   return p
 end
 
-"set_c!(prob, c) — TAD.jl:844-872"
+"set_c!(prob, c) — TAD.jl:844-872; a 2-D c given to a layered problem is repeated over the layers (TAD.jl:865)"
 function set_c!(p::Prob, c::Array{Float64})
-  GC.@preserve c check(ccall((:ptf_set_c, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), p.h, c, 0), p.h)
+  replicate = (p.nbatch > 1 && ndims(c) == p.ndim) ? 1 : 0
+  GC.@preserve c check(ccall((:ptf_set_c, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), p.h, c, replicate), p.h)
   updatevars!(p)
 end
 
@@ -214,10 +216,28 @@ function step_until!(p::MQGProb, t)
 end
 
 """
-Problem(MQGprob; κ, η, stepper, tracer_release_time) — TAD.jl:225-250.  `tracer` is the layered tracer problem created
-with nbatch = nlayers and PTF_FLOW_LAYERED; after this call its calcN! reads MQGprob.vars.u .+ params.U and vars.v
-(TAD.jl:795-796) directly from the flow solver's device buffers.
+Problem(MQGprob; κ, η, stepper, tracer_release_time) — TAD.jl:225-250: the layered tracer problem on the flow's grid and
+dt (flow_kind = PTF_FLOW_LAYERED, nbatch = nlayers, one velocity field per layer), coupled to the device-resident flow:
+its calcN! reads MQGprob.vars.u .+ params.U and vars.v (TAD.jl:795-796) directly from the flow solver's device buffers.
 """
+function Problem(flow::MQGProb; κ=0.1, η=κ, stepper="FilteredRK4", tracer_release_time=0, Lx=2π, Ly=Lx, device=-1)
+  d = PtfDesc()
+  check(ccall((:ptf_desc_init, LIB), Int32, (Ref{PtfDesc},), d))
+  d.ndim = 2; d.n = (flow.nx, flow.ny, 1); d.L = (Lx, Ly, 1.0); d.kappa = (κ, η, κ)
+  d.dt = flow.clock.dt; d.stepper = stepper_id(stepper); d.device = device
+  d.flow_kind = 3                                # PTF_FLOW_LAYERED
+  d.nbatch = flow.nlayers; d.velocity_per_batch = 1
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:ptf_create, LIB), Int32, (Ref{PtfDesc}, Ref{Ptr{Cvoid}}), d, h))
+  dims, sdims = (flow.nx, flow.ny, flow.nlayers), (flow.nx ÷ 2 + 1, flow.ny, flow.nlayers)
+  p = Prob(h[], zeros(ComplexF64, sdims), Clock(flow.clock.dt, 0.0, 0), Vars(zeros(dims), zeros(ComplexF64, sdims)),
+           (flow.nx, flow.ny, 1), (Lx, Ly, 1.0), 2, nothing, flow.nlayers)
+  finalizer(q -> ccall((:ptf_destroy, LIB), Int32, (Ptr{Cvoid},), q.h), p)
+  couple!(p, flow; tracer_release_time=tracer_release_time)
+  return p
+end
+
+"couples an existing layered tracer problem to the flow (what Problem(MQGprob; …) does after creating it)"
 function couple!(tracer::Prob, flow::MQGProb; tracer_release_time=0)
   tracer_release_time < 0 && throw(ArgumentError("tracer_release_time must be non-negative!"))   # TAD.jl:234
   tracer_release_time > 0 && step_until!(flow, tracer_release_time)                                # TAD.jl:236-239
