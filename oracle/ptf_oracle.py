@@ -164,8 +164,8 @@ def aliased_ranges(n, nk, aliased_fraction, r2c):
     """0-based [lo, hi) index range FourierFlows ``getaliasedwavenumbers`` zeroes on one axis."""
     iL = int(math.floor((1 - aliased_fraction) / 2 * n)) + 1     # 1-based inclusive
     iR = int(math.ceil((1 + aliased_fraction) / 2 * n))          # 1-based inclusive
-    if aliased_fraction <= 0:   # FF: kalias = nk/2 + 1, kralias = nkr — only the Nyquist index is zeroed
-        return (nk - 1, nk) if r2c else (n // 2, n // 2 + 1)
+    if aliased_fraction <= 0:   # FF dealias!: `grid.aliased_fraction == 0 && return nothing` — no mode is zeroed
+        return (0, 0)           # [UPSTREAM-RECALLED, FourierFlows 0.10 src/domains.jl; ADVICE r01]
     if r2c:
         return (iL - 1, nk)
     return (iL - 1, iR)

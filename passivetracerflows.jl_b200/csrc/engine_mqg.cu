@@ -57,6 +57,14 @@ __global__ void __launch_bounds__(128) k_mqg_spec(MqgSpecArgs a) {
       if (a.uniform_bg) {   // rfft(v*Qy_j) = Qy_j * i kr psi-hat_j (v = irfft(i kr psi-hat), Qy_j a constant); u*Qx = 0
         const double2 pj = a.psih[(int64_t)j * plane + i];
         f0 = make_double2(-a.qy[j] * kx * pj.y, a.qy[j] * kx * pj.x);
+        if (ix == a.nkr - 1) {
+          // x-Nyquist column: the c2r that produced v dropped Im of this column after the y transform, i.e. v carries
+          // the y-Hermitian part (W(l) + conj W(-l)) / 2 of W = i kr psi-hat only.  Invisible while dealias! zeroes the
+          // column; with aliased_fraction = 0 (FourierFlows: no-op mask, the example's setting) it is 6.5e-8 of the state.
+          const double2 pm = a.psih[(int64_t)j * plane + ((a.ny - iy) % a.ny) * a.nkr + ix];
+          const double wx = -a.qy[j] * kx * pm.y, wy = a.qy[j] * kx * pm.x;
+          f0 = make_double2(0.5 * (f0.x + wx), 0.5 * (f0.y - wy));
+        }
       } else {
         f0 = a.spec3[(0 * NL + j) * plane + i];
       }
@@ -276,10 +284,10 @@ class MqgSolver {
       ax.ax_lo = (int64_t)std::floor((1.0 - a) / 2.0 * (double)nx);
       ax.ay_lo = (int64_t)std::floor((1.0 - a) / 2.0 * (double)ny);
       ax.ay_hi = (int64_t)std::ceil((1.0 + a) / 2.0 * (double)ny);
-    } else {       // aliased_fraction = 0 still zeroes the Nyquist index
-      ax.ax_lo = nx / 2;
-      ax.ay_lo = ny / 2;
-      ax.ay_hi = ny / 2 + 1;
+    } else {       // FF dealias!: `grid.aliased_fraction == 0 && return nothing` — the mask is empty (examples/…:57)
+      ax.ax_lo = nx / 2 + 1;
+      ax.ay_lo = 0;
+      ax.ay_hi = 0;
     }
     hkx = kx;
     hky = ky;

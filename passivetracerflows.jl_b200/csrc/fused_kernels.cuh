@@ -725,23 +725,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
     for (int e = 0; e < 8; ++e) prefetch_l2(Cb + e * se);
   }
 
-#ifndef PTF_X_EXP
-#define PTF_X_EXP 0   // compile-time experiment bits of the row kernel (build.py --variant): 4, 8 below
-#endif
-  if (!D3 && (PTF_X_EXP & 4)) {   // experiment: the second gather batch is pulled into L2 while the first one is in flight
-#pragma unroll
-    for (int j = GB; j < 8; ++j) {
-      prefetch_l2(Ab + (size_t)(t + T * j) * ny);
-      prefetch_l2(Bb + (size_t)(t + T * j) * ny);
-    }
-  }
-  if (!D3 && VMODE == 3 && (PTF_X_EXP & 8) && (t & 3) == 0) {   // experiment: row 1's velocities requested up front too
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      prefetch_l2(a.va.arr[0] + voff + NX + t + T * e);
-      prefetch_l2(a.va.arr[1] + voff + NX + t + T * e);
-    }
-  }
   // row 0's inputs, and the parking of row 1's
 #pragma unroll
   for (int h = 0; h < 8 / GB; ++h) {  // batches of GB k's: 2*GB 256-bit requests in flight per thread

@@ -247,12 +247,10 @@ void build_context(ptf_handle* h, const ptf_desc* d) {
     ax.ay_hi = hi(g.ny);
     ax.az_lo = lo(g.nz);
     ax.az_hi = hi(g.nz);
-    if (a <= 0.0) {  // FF: kalias = nk/2 + 1, kralias = nkr — aliased_fraction = 0 still zeroes the Nyquist index
-      ax.ax_lo = g.nx / 2;
-      ax.ay_lo = g.ny / 2;
-      ax.ay_hi = g.ny / 2 + 1;
-      ax.az_lo = g.nz / 2;
-      ax.az_hi = g.nz / 2 + 1;
+    if (a <= 0.0) {  // FF dealias!: `grid.aliased_fraction == 0 && return nothing` — nothing is zeroed (empty ranges)
+      ax.ax_lo = g.nkr;
+      ax.ay_lo = ax.ay_hi = 0;
+      ax.az_lo = ax.az_hi = 0;
     }
   }
 }
