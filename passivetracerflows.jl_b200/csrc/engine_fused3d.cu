@@ -180,7 +180,7 @@ class Fused3DEngine final : public Engine {
     const size_t nreal = (size_t)nx * ny * nzl;
     for (auto& b : sepv)
       if (b.n != nreal) b.alloc(nreal, &dev_bytes);
-    k_sep_fill<<<148 * 16, 256, 0, ctx.stream>>>(vs.va, sepv[0].p, sepv[1].p, sepv[2].p, nx, ny, nzl, nz, (int)g.zoff);
+    k_sep_fill<<<148 * 8, 256, 0, ctx.stream>>>(vs.va, sepv[0].p, sepv[1].p, sepv[2].p, nx, ny, nzl, nz, (int)g.zoff);
     ++own_launches;
     sep_dirty = false;
   }

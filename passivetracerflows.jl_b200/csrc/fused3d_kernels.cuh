@@ -223,16 +223,33 @@ __global__ void __launch_bounds__(32) k_xbarrier(unsigned* __restrict__ local, X
 // The velocity is frozen at clock.t for all stages of a step (TAD.jl:737), so the three fields are evaluated ONCE per
 // step (24 B/pt, ~4 % of a step's traffic) and the row kernel reads them like steady arrays; evaluating the sums
 // per point inside the row kernel costs 2-4 table loads per point and component and was measured 3x slower.
+// One (y, z) row per block iteration: the row's coefficients a_m(t) Y_m(y) Z_m(z) are formed once (shared memory), every
+// point then costs one table load and one FMA per term and component.
 __global__ void __launch_bounds__(256) k_sep_fill(VelArgs va, double* __restrict__ u, double* __restrict__ v,
                                                   double* __restrict__ w, int nx, int ny, int nzl, int nzg, int zoff) {
-  const int64_t n = (int64_t)nx * ny * nzl;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % nx);
-    const int y = (int)((i / nx) % ny);
-    const int z = (int)(i / ((int64_t)nx * ny)) + zoff;
-    u[i] = sep_eval(va.sep[0], x, y, z, nx, ny, nzg, 3);
-    v[i] = sep_eval(va.sep[1], x, y, z, nx, ny, nzg, 3);
-    w[i] = sep_eval(va.sep[2], x, y, z, nx, ny, nzg, 3);
+  __shared__ double cs[3][MAX_TERMS];
+  double* const out[3] = {u, v, w};
+  const int64_t rows = (int64_t)ny * nzl;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = (int)(row % ny);
+    const int z = (int)(row / ny) + zoff;
+    __syncthreads();   // previous row's readers are done
+    if (threadIdx.x < 3 * MAX_TERMS) {
+      const int c = threadIdx.x / MAX_TERMS, m = threadIdx.x % MAX_TERMS;
+      const SepFlow& f = va.sep[c];
+      cs[c][m] = m < f.nterms ? f.a[m] * f.yt[(int64_t)m * ny + y] * f.zt[(int64_t)m * nzg + z] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const SepFlow& f = va.sep[c];
+      double* o = out[c] + row * nx;
+      for (int x = threadIdx.x; x < nx; x += blockDim.x) {
+        double acc = 0.0;
+        for (int m = 0; m < f.nterms; ++m) acc += cs[c][m] * f.xt[(int64_t)m * nx + x];
+        __stcg(o + x, acc);
+      }
+    }
   }
 }
 

@@ -4,6 +4,11 @@
 #error "compile with -DPTF_INST_N=<transform length>"
 #endif
 #include "fused3d_kernels.cuh"
+#ifdef PTF_FFT_EXPERIMENTS
+namespace ptf {
+#include "../../microbench/fft_experiments.cuh"
+}
+#endif
 
 #define PTF_CAT2(a, b) a##b
 #define PTF_CAT(a, b) PTF_CAT2(a, b)
@@ -38,14 +43,16 @@ void FN(fused3_launch_y_)(bool inverse, const void* y3args, cudaStream_t st, int
 }
 #endif
 
-// transform self-test + the timing experiments recorded in profiles/r01_fft_core_experiments.md
+// transform self-test (tests/test_gpu_fused.py::test_fft_core_matches_numpy).  The timing experiments of
+// profiles/r01_fft_core_experiments.md live in microbench/fft_experiments.cuh (-DPTF_FFT_EXPERIMENTS builds only).
 void FN(fused_selftest_)(int dir, int count, const double2* in, double2* out, const void* twp) {
   constexpr int NN = PTF_INST_N;
   constexpr int F = 256 / Cfg<NN>::T;
   const Twiddles tw = *static_cast<const Twiddles*>(twp);
   const size_t sm = y_smem<NN>() + g_smem_pad;
-  const size_t total = (size_t)NN * count;
   const int blocks = (count + F - 1) / F;
+#ifdef PTF_FFT_EXPERIMENTS
+  const size_t total = (size_t)NN * count;
   const bool timing = std::getenv("PTF_SELFTEST_TIME") != nullptr;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
@@ -66,63 +73,70 @@ void FN(fused_selftest_)(int dir, int count, const double2* in, double2* out, co
       fprintf(stderr, "[selftest_fft] pair gather+scatter via TMEM n=%d count=%d  %.4f ms  %.0f GB/s (R+W)\n", NN, count,
               ms, gb / ms * 1e3);
     }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return;
+  }
+#else
+  if (dir == 2) throw Error(PTF_EUNSUPPORTED, "the TMEM pairing experiment needs a -DPTF_FFT_EXPERIMENTS build");
+#endif
+  if (dir < 0) {
+    allow_smem(k_fft_test<NN, -1>, sm);
+    k_fft_test<NN, -1><<<blocks, 256, sm>>>(in, out, count, tw);
   } else {
-    if (dir < 0) {
-      allow_smem(k_fft_test<NN, -1>, sm);
-      k_fft_test<NN, -1><<<blocks, 256, sm>>>(in, out, count, tw);
-    } else {
-      allow_smem(k_fft_test<NN, +1>, sm);
-      k_fft_test<NN, +1><<<blocks, 256, sm>>>(in, out, count, tw);
+    allow_smem(k_fft_test<NN, +1>, sm);
+    k_fft_test<NN, +1><<<blocks, 256, sm>>>(in, out, count, tw);
+  }
+#ifdef PTF_FFT_EXPERIMENTS
+  if (timing && count % F == 0) {
+    cudaDeviceSynchronize();
+    const int reps = 10;
+    cudaEventRecord(e0);
+    for (int r = 0; r < reps; ++r) {
+      if (dir < 0) k_fft_test<NN, -1><<<blocks, 256, sm>>>(in, out, count, tw);
+      else k_fft_test<NN, +1><<<blocks, 256, sm>>>(in, out, count, tw);
     }
-    if (timing && count % F == 0) {
-      cudaDeviceSynchronize();
-      const int reps = 10;
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= reps;
+    fprintf(stderr, "[selftest_fft] n=%d count=%d  %.4f ms  %.0f GB/s (R+W)\n", NN, count, ms, gb / ms * 1e3);
+    if (const char* rp = std::getenv("PTF_SELFTEST_REPEAT")) {
+      const int rep = std::atoi(rp);
+      allow_smem(k_fft_rate_test<NN>, sm);
+      k_fft_rate_test<NN><<<blocks, 256, sm>>>(in, out, count, tw, rep);
+      cudaEventRecord(e0);
+      k_fft_rate_test<NN><<<blocks, 256, sm>>>(in, out, count, tw, rep);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double nfft = (double)count * rep;
+      fprintf(stderr,
+              "[selftest_fft] compute-only n=%d: %d x %d transforms in %.4f ms -> %.1f transforms/us (chip), %.0f "
+              "cycles/transform/SM @1.9GHz\n",
+              NN, count, rep, ms, nfft / (ms * 1e3), ms * 1e-3 * 1.9e9 * 148 / nfft);
+    }
+    for (int pair = 0; pair < 2; ++pair) {
+      if (pair == 0) allow_smem(k_fft_gather_test<NN, 0>, sm);
+      else allow_smem(k_fft_gather_test<NN, 1>, sm);
       cudaEventRecord(e0);
       for (int r = 0; r < reps; ++r) {
-        if (dir < 0) k_fft_test<NN, -1><<<blocks, 256, sm>>>(in, out, count, tw);
-        else k_fft_test<NN, +1><<<blocks, 256, sm>>>(in, out, count, tw);
+        if (pair == 0) k_fft_gather_test<NN, 0><<<blocks, 256, sm>>>(in, out, count, tw);
+        else k_fft_gather_test<NN, 1><<<blocks, 256, sm>>>(in, out, count, tw);
       }
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);
       cudaEventElapsedTime(&ms, e0, e1);
       ms /= reps;
-      fprintf(stderr, "[selftest_fft] n=%d count=%d  %.4f ms  %.0f GB/s (R+W)\n", NN, count, ms, gb / ms * 1e3);
-      if (const char* rp = std::getenv("PTF_SELFTEST_REPEAT")) {
-        const int rep = std::atoi(rp);
-        allow_smem(k_fft_rate_test<NN>, sm);
-        k_fft_rate_test<NN><<<blocks, 256, sm>>>(in, out, count, tw, rep);
-        cudaEventRecord(e0);
-        k_fft_rate_test<NN><<<blocks, 256, sm>>>(in, out, count, tw, rep);
-        cudaEventRecord(e1);
-        cudaEventSynchronize(e1);
-        cudaEventElapsedTime(&ms, e0, e1);
-        const double nfft = (double)count * rep;
-        fprintf(stderr,
-                "[selftest_fft] compute-only n=%d: %d x %d transforms in %.4f ms -> %.1f transforms/us (chip), %.0f "
-                "cycles/transform/SM @1.9GHz\n",
-                NN, count, rep, ms, nfft / (ms * 1e3), ms * 1e-3 * 1.9e9 * 148 / nfft);
-      }
-      for (int pair = 0; pair < 2; ++pair) {
-        if (pair == 0) allow_smem(k_fft_gather_test<NN, 0>, sm);
-        else allow_smem(k_fft_gather_test<NN, 1>, sm);
-        cudaEventRecord(e0);
-        for (int r = 0; r < reps; ++r) {
-          if (pair == 0) k_fft_gather_test<NN, 0><<<blocks, 256, sm>>>(in, out, count, tw);
-          else k_fft_gather_test<NN, 1><<<blocks, 256, sm>>>(in, out, count, tw);
-        }
-        cudaEventRecord(e1);
-        cudaEventSynchronize(e1);
-        cudaEventElapsedTime(&ms, e0, e1);
-        ms /= reps;
-        fprintf(stderr, "[selftest_fft] gather-in (pair=%d)       %.4f ms  %.0f GB/s (R+W)\n", pair, ms, gb / ms * 1e3);
-      }
-      // the experiments overwrite `out`: recompute the requested transform last
-      if (dir < 0) k_fft_test<NN, -1><<<blocks, 256, sm>>>(in, out, count, tw);
-      else k_fft_test<NN, +1><<<blocks, 256, sm>>>(in, out, count, tw);
+      fprintf(stderr, "[selftest_fft] gather-in (pair=%d)       %.4f ms  %.0f GB/s (R+W)\n", pair, ms, gb / ms * 1e3);
     }
+    // the experiments overwrite `out`: recompute the requested transform last
+    if (dir < 0) k_fft_test<NN, -1><<<blocks, 256, sm>>>(in, out, count, tw);
+    else k_fft_test<NN, +1><<<blocks, 256, sm>>>(in, out, count, tw);
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+#endif
 }
 
 }  // namespace ptf

@@ -1,3 +1,4 @@
+# needs the experiments build: python passivetracerflows.jl_b200/build.py --variant exp PTF_FFT_EXPERIMENTS=1 ; PTF_LIB_PATH=.../libptf_b200_exp.so
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

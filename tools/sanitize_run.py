@@ -1,3 +1,4 @@
+# needs the experiments build: python passivetracerflows.jl_b200/build.py --variant exp PTF_FFT_EXPERIMENTS=1 ; PTF_LIB_PATH=.../libptf_b200_exp.so
 """Small driver for compute-sanitizer: one fused 2-D step per stepper family + the 1-D engine + FFT self-tests."""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
