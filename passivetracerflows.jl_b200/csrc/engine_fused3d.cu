@@ -383,7 +383,8 @@ class Fused3DEngine final : public Engine {
     a.YC = YC.p;
     a.PX = PX;
     a.PXY = PXY;
-    a.ky = ctx.ax.ky;
+    a.cy = ctx.ax.cy;
+    a.nyq_sign = ctx.ax.nyq_sign;
     a.tw = tw_y();
     a.nkx = nkx;
     a.nyl = nyl;

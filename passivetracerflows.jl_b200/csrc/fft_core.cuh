@@ -105,6 +105,23 @@ PTF_HD void dft8(double2& x0, double2& x1, double2& x2, double2& x3, double2& x4
 PTF_HD constexpr int pad_idx(int i) { return i + (i >> 4); }
 
 #ifdef __CUDACC__
+// Wavenumber of element l = t + T*e (T = N/16) of an fftfreq-ordered axis of length N, k = (double)j * c with
+// j = l (l < N/2) or l - N: bit-identical to the host-built table (one correctly rounded product of an exact integer),
+// without the table load.  e is a compile-time constant at every call site, so j = t + const.
+template <int N>
+__device__ __forceinline__ double wavenumber_full(int t, int e, double c, int nyq_sign) {
+  constexpr int T = N / 16;
+  const double j = (double)t + (double)(T * e - (e >= 8 ? N : 0));
+  double k = j * c;
+  if (e == 8 && nyq_sign > 0 && t == 0) k = -k;   // l == N/2 stored positive on request
+  return k;
+}
+// same for the r2c axis (k = l * c, l <= N/2)
+template <int N>
+__device__ __forceinline__ double wavenumber_half(int t, int e, double c) {
+  return ((double)t + (double)((N / 16) * e)) * c;
+}
+
 // Value barrier for the optimiser: the result is "a different value" as far as common-subexpression elimination and
 // loop-invariant code motion can tell.  Used on gather strides / bases so that 16 precomputed 64-bit addresses are
 // not kept live across a transform (32 registers = spills at 128 registers per thread); recomputing them is 1 IMAD each.

@@ -31,7 +31,8 @@ struct Y3Args {
   double2 *YA, *YB, *YC;  // [zl][kr][y]
   const double2* PX;   // [zl][y/8][kr][y%8]
   double2* PXY;        // [p][kr][zl/8][ll][zl%8]
-  const double* ky;    // [ny] global
+  double cy;           // generating constant of the ky table (fft::wavenumber_full)
+  int nyq_sign;
   Twiddles tw;
   int nkx, nyl, nzl;
   // element l = t + T*e of a y column lives in the block of rank e >> esh (nyl is a multiple of T = ny/16 for P <= 16):
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_yinv3(Y3Args a) {
     if (it == 0 || it == 2) {   // the y derivative of this plane, parked until A's transform is stored
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const double ky = a.ky[t + T * e];
+        const double ky = fft::wavenumber_full<NY>(t, e, a.cy, a.nyq_sign);
         tmem::st1(t_b + 4 * e, make_double2(-ky * v[e].y, ky * v[e].x));
       }
       tmem::wait_st();

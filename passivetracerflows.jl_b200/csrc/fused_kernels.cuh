@@ -97,7 +97,8 @@ __device__ __forceinline__ bool col_dealiased(const AxisTables& ax, int kr, int 
 struct ColId {
   int kr, lp;        // kr index; 3-D: GLOBAL ky index of this column (0 in 2-D)
   double kx, kyp;    // their wavenumbers
-  const double* kax; // wavenumber table of the transform axis
+  double cax;        // generating constant of the transform axis' wavenumbers (fft::wavenumber_full)
+  int nyq;           // its Nyquist sign switch
 };
 
 // ---- RK4 family (FF RK4substeps!/RK4update!).  N^ (t_nh) and the new stage state s' (t_w) live in TMEM, so a
@@ -136,7 +137,7 @@ __device__ __forceinline__ void rk4_stage(const YArgs& a, uint32_t t_nh, uint32_
       for (int jj = 0; jj < 4; ++jj) {
         const int j = j0 + jj, e = e0 + j, l = t + T * e;
         const size_t i = col + l;
-        const double L = col_lin<D3>(a.ax, kx, c.kyp, c.kax[l]);
+        const double L = col_lin<D3>(a.ax, kx, c.kyp, fft::wavenumber_full<NY>(t, e, c.cax, c.nyq));
         const double2 Nh = nh[jj];
         const bool dm = DM && col_dealiased<D3>(a.ax, c.kr, c.lp, l);
         double2 next;
@@ -276,13 +277,14 @@ __device__ __forceinline__ void fused_y_column(const YArgs& a, const int cid_raw
     ll = cid - c.kr * a.nyl;
     c.lp = a.yoff + ll;
     c.kyp = a.ax.ky[c.lp];
-    c.kax = a.ax.kz;
+    c.cax = a.ax.cz;
   } else {
     c.kr = cid;
     c.lp = 0;
     c.kyp = 0.0;
-    c.kax = a.ax.ky;
+    c.cax = a.ax.cy;
   }
+  c.nyq = a.ax.nyq_sign;
   c.kx = a.ax.kx[c.kr];
   const double kx = c.kx;
   double2 w[16];
@@ -290,7 +292,7 @@ __device__ __forceinline__ void fused_y_column(const YArgs& a, const int cid_raw
   if (HAS_IN && FAM != FAM_OTHER && a.C.filtered && (a.C.mode == CM_RK4_S4 || a.C.mode == CM_ETD_S4)) {
 #pragma unroll 1
     for (int e = 0; e < 16; ++e) {
-      const double ka = c.kax[t + T * e];
+      const double ka = fft::wavenumber_full<NY>(t, e, c.cax, c.nyq);
       fl[e] = D3 ? filter_slow(kx * a.ax.fx, c.kyp * a.ax.fy, ka * a.ax.fz, a.ax.f_inner, a.ax.f_decay, a.ax.f_order)
                  : filter_slow(kx * a.ax.fx, ka * a.ax.fy, 0.0, a.ax.f_inner, a.ax.f_decay, a.ax.f_order);
     }
@@ -381,7 +383,7 @@ __device__ __forceinline__ void fused_y_column(const YArgs& a, const int cid_raw
         if (active) {
           // ForwardEuler / LSRK54 / AB3 evaluate calcN at sol itself: dealias!(sol) acts in place before the combine
           if (dm && a.C.mode != CM_STORE) a.P.s0[col + l] = make_double2(0.0, 0.0);
-          const double ka = c.kax[l];
+          const double ka = fft::wavenumber_full<NY>(t, e, c.cax, c.nyq);
           nx = combine_at<CMASK_OTHER>(a.P, a.C, a.ax, col + l, ccol + l, kx, D3 ? c.kyp : ka, D3 ? ka : 0.0,
                                        v[out_slot<NY>(e)]);
         }
@@ -417,7 +419,7 @@ __device__ __forceinline__ void fused_y_column(const YArgs& a, const int cid_raw
       tmem::ldn<4>(t_w + 16 * q, r4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double ky = c.kax[t + T * (4 * q + j)];
+        const double ky = fft::wavenumber_full<NY>(t, 4 * q + j, c.cax, c.nyq);
         w[4 * q + j] = make_double2(-ky * r4[j].y, ky * r4[j].x);
       }
     }
@@ -427,7 +429,7 @@ __device__ __forceinline__ void fused_y_column(const YArgs& a, const int cid_raw
       const int l = t + T * e;
       double2 s = __ldcg(a.next_state + col + l);
       if (DM && col_dealiased<D3>(a.ax, c.kr, c.lp, l)) s = make_double2(0.0, 0.0);
-      double ky = c.kax[l] * a.inv_n;
+      double ky = fft::wavenumber_full<NY>(t, e, c.cax, c.nyq) * a.inv_n;
       w[e] = make_double2(-ky * s.y, ky * s.x);
     }
   }
@@ -499,11 +501,11 @@ struct XArgs {
 // Z = X + iY with X = i*kr*A (-> gx), Y = B (-> gy) for the lower half k = t + T*e < NX/2; the mirrored bin NX-k
 // gets conj(X) + i*conj(Y) and is handed to its owner through shared memory.
 template <int NX>
-__device__ __forceinline__ void x_lower(double2& ve, int e, int t, double2 Av, double2 Bv,
-                                        const double* __restrict__ kxt, double2* __restrict__ sm) {
+__device__ __forceinline__ void x_lower(double2& ve, int e, int t, double2 Av, double2 Bv, double cx,
+                                        double2* __restrict__ sm) {
   constexpr int T = Cfg<NX>::T;
   const int k = t + T * e;
-  const double kx = kxt[k];
+  const double kx = fft::wavenumber_half<NX>(t, e, cx);   // = the kr table entry, without the load
   const double Xx = -kx * Av.y, Xy = kx * Av.x;
   if (e == 0 && t == 0) {
     ve = make_double2(Xx, Bv.x);  // c2r ignores the imaginary part of the DC bin
@@ -527,13 +529,13 @@ __device__ __forceinline__ void x_lower_plain(double2& ve, int e, int t, double2
 }
 // bin k = NX/2: real part only (c2r semantics)
 template <int NX>
-__device__ __forceinline__ void x_nyquist(int t, const double2* Ab, const double2* Bb, int ny, int q,
-                                          const double* __restrict__ kxt, double2* __restrict__ sm) {
+__device__ __forceinline__ void x_nyquist(int t, const double2* Ab, const double2* Bb, int ny, int q, double cx,
+                                          double2* __restrict__ sm) {
   constexpr int H = NX / 2;
   if (t == 0) {
     double2 Av = __ldcg(Ab + (size_t)H * ny + q);
     double2 Bv = __ldcg(Bb + (size_t)H * ny + q);
-    sm[pad_idx(H)] = make_double2(-kxt[H] * Av.y, Bv.x);
+    sm[pad_idx(H)] = make_double2(-((double)H * cx) * Av.y, Bv.x);
   }
 }
 // velocity row -> TMEM (its latency hides behind the inverse transform that follows)
@@ -741,7 +743,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
       tmem::st1(t_in + 8 * (GB * h + j) + 4, B1[j]);
     }
 #pragma unroll
-    for (int j = 0; j < GB; ++j) x_lower<NX>(v[GB * h + j], GB * h + j, t, A0[j], B0[j], a.ax.kx, sm);
+    for (int j = 0; j < GB; ++j) x_lower<NX>(v[GB * h + j], GB * h + j, t, A0[j], B0[j], a.ax.cx, sm);
   }
   constexpr int NQ = D3 ? 3 : 2;   // 3-D: a third pass of the same loop transforms (gz row 0, gz row 1)
 #pragma unroll 1
@@ -753,8 +755,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
       for (int h = 0; h < 4; ++h) {
         double2 AB[4];  // (A1, B1) of k-slots 2h, 2h+1
         tmem::ldn<4>(t_in + 16 * h, AB);
-        x_lower<NX>(v[2 * h], 2 * h, t, AB[0], AB[1], a.ax.kx, sm);
-        x_lower<NX>(v[2 * h + 1], 2 * h + 1, t, AB[2], AB[3], a.ax.kx, sm);
+        x_lower<NX>(v[2 * h], 2 * h, t, AB[0], AB[1], a.ax.cx, sm);
+        x_lower<NX>(v[2 * h + 1], 2 * h + 1, t, AB[2], AB[3], a.ax.cx, sm);
       }
       if constexpr (D3) {        // the parking slot is free again: fetch the (C row 0, C row 1) pairs into it
         const double2* Cb = a.Cf + (size_t)b * a.nkr * ny + 2 * pair + (size_t)t * ny;
@@ -789,11 +791,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
         }
         x_request_uv<NX, VMODE, true, true>(a, voff, 0, t, t_uv);
       } else {
-        x_nyquist<NX>(t, Ab, Bb, ny, q, a.ax.kx, sm);
+        x_nyquist<NX>(t, Ab, Bb, ny, q, a.ax.cx, sm);
         x_request_uv<NX, VMODE, false, true>(a, voff, q, t, t_uv);
       }
     } else {
-      x_nyquist<NX>(t, Ab, Bb, ny, q, a.ax.kx, sm);
+      x_nyquist<NX>(t, Ab, Bb, ny, q, a.ax.cx, sm);
       x_request_uv<NX, VMODE>(a, voff, q, t, t_uv);  // includes tcgen05.wait::st for the parked inputs as well
     }
     fft::group_sync<T, NT>(grp);

@@ -224,6 +224,10 @@ void build_context(ptf_handle* h, const ptf_desc* d) {
   ax.kx = c.d_kx.p;
   ax.ky = c.d_ky.p;
   ax.kz = c.d_kz.p;
+  ax.cx = (2.0 * M_PI / g.Lx * (double)g.nx) / (double)g.nx;   // the same expressions as rfft_/fft_wavenumbers
+  ax.cy = (2.0 * M_PI / g.Ly * (double)g.ny) / (double)g.ny;
+  ax.cz = (2.0 * M_PI / g.Lz * (double)g.nz) / (double)g.nz;
+  ax.nyq_sign = d->nyquist_sign;
   ax.kappa = d->kappa[0];
   ax.eta = d->kappa[1];
   ax.iota = d->kappa[2];

@@ -112,6 +112,11 @@ struct AxisTables {
   const double* kx = nullptr;  // [nkr]
   const double* ky = nullptr;  // [ny]
   const double* kz = nullptr;  // [nz]
+  // the tables' generating constants: k_a[i] = (double)j * c_a with j = i (r2c axis) or fftfreq order (j = i - n for
+  // i >= n/2), exactly as the host builds them — the fused kernels recompute their 16 wavenumbers per thread from
+  // these instead of loading them (bit-identical; no L1/L2 latency in front of the combine)
+  double cx = 0, cy = 0, cz = 0;
+  int nyq_sign = -1;           // > 0: the y/z Nyquist wavenumber is stored positive (ptf_desc.nyquist_sign)
   // kappa*kx^2 etc. are formed in-kernel in the reference's operation order.
   double kappa = 0, eta = 0, iota = 0, kappa_h = 0;
   int n_kappa_h = 0;
