@@ -79,9 +79,15 @@ __device__ __noinline__ double filter_slow(double a, double b, double c, double 
   double Ksq = a * a;
   Ksq += b * b;
   Ksq += c * c;
+  if (Ksq < f_inner * f_inner) return 1.0;   // (K < f_inner for the non-negative K: no square root for the untouched modes)
   double K = sqrt(Ksq);
   if (K < f_inner) return 1.0;
-  return exp(-f_decay * pow(K - f_inner, f_order));
+  const double d = K - f_inner;
+  if (f_order == 4.0) {   // FourierFlows' default order: two multiplies instead of the general pow()
+    const double d2 = d * d;
+    return exp(-f_decay * (d2 * d2));
+  }
+  return exp(-f_decay * pow(d, f_order));
 }
 
 // One column of the column kernel: 2-D = (kr; transform axis y), 3-D = (kr, ky row lp; transform axis z).
@@ -285,7 +291,7 @@ __device__ __forceinline__ void fused_y_column(const YArgs& a, const int cid_raw
     c.cax = a.ax.cy;
   }
   c.nyq = a.ax.nyq_sign;
-  c.kx = a.ax.kx[c.kr];
+  c.kx = (double)c.kr * a.ax.cx;   // = a.ax.kx[c.kr], without the load
   const double kx = c.kx;
   double2 w[16];
   double fl[16];  // FourierFlows filter of this thread's 16 modes (final stage of Filtered* steppers only)
