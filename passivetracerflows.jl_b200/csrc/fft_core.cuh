@@ -182,26 +182,43 @@ PTF_HD void twiddle15(double2 (&v)[16], double2 w1, double2 w2, double2 w4, doub
 #ifdef __CUDACC__
 // Last Stockham pass: radix R3 over sub-transforms of length NS (= N / R3); work item q of thread t is element
 // j = t + q*T, uses register slots q + r*S, twiddles w_N^(r*k) with k = j mod NS read from tab[m*NS + k] = w_N^(2^m k).
-template <int N, int DIR, int NS>
-__device__ __forceinline__ void last_pass(double2 (&v)[16], int t, const double2* __restrict__ tab) {
-  constexpr int T = Cfg<N>::T, R3 = Cfg<N>::R3, S = Cfg<N>::S;
+// The table entries are fetched by last_pass_load BEFORE the exchange barrier that precedes the pass (the data registers
+// are in shared memory at that point, so the loads cost no register pressure and their latency hides behind the barrier).
+template <int N>
+struct LastTw {
+  static constexpr int R3 = Cfg<N>::R3, S = Cfg<N>::S;
+  static constexpr int NW = R3 == 2 ? 1 : (R3 == 4 ? 2 : (R3 == 8 ? 3 : 4));
+  double2 w[S > 0 ? S : 1][NW];
+};
+template <int N, int NS>
+__device__ __forceinline__ void last_pass_load(LastTw<N>& W, int t, const double2* __restrict__ tab) {
+  constexpr int T = Cfg<N>::T, S = Cfg<N>::S;
 #pragma unroll
   for (int q = 0; q < S; ++q) {
     const int k = (t + q * T) & (NS - 1);
-    double2 w1 = __ldg(&tab[k]);
+#pragma unroll
+    for (int m = 0; m < LastTw<N>::NW; ++m) W.w[q][m] = __ldg(&tab[m * NS + k]);
+  }
+}
+template <int N, int DIR>
+__device__ __forceinline__ void last_pass(double2 (&v)[16], const LastTw<N>& W) {
+  constexpr int R3 = Cfg<N>::R3, S = Cfg<N>::S;
+#pragma unroll
+  for (int q = 0; q < S; ++q) {
+    const double2 w1 = W.w[q][0];
     if (R3 == 2) {
       v[q + S] = twmul<DIR>(v[q + S], w1);
       dft2(v[q], v[q + S]);
     } else if (R3 == 4) {
-      double2 w2 = __ldg(&tab[NS + k]);
+      const double2 w2 = W.w[q][LastTw<N>::NW > 1 ? 1 : 0];
       double2 w3 = cmul2(w1, w2);
       v[q + S] = twmul<DIR>(v[q + S], w1);
       v[q + 2 * S] = twmul<DIR>(v[q + 2 * S], w2);
       v[q + 3 * S] = twmul<DIR>(v[q + 3 * S], w3);
       dft4<DIR>(v[q], v[q + S], v[q + 2 * S], v[q + 3 * S]);
     } else if (R3 == 8) {
-      double2 w2 = __ldg(&tab[NS + k]);
-      double2 w4 = __ldg(&tab[2 * NS + k]);
+      const double2 w2 = W.w[q][LastTw<N>::NW > 1 ? 1 : 0];
+      const double2 w4 = W.w[q][LastTw<N>::NW > 2 ? 2 : 0];
       double2 w3 = cmul2(w1, w2), w5 = cmul2(w4, w1), w6 = cmul2(w4, w2);
       double2 w7 = cmul2(w4, w3);
       v[q + S] = twmul<DIR>(v[q + S], w1);
@@ -213,9 +230,9 @@ __device__ __forceinline__ void last_pass(double2 (&v)[16], int t, const double2
       v[q + 7 * S] = twmul<DIR>(v[q + 7 * S], w7);
       dft8<DIR>(v[q], v[q + S], v[q + 2 * S], v[q + 3 * S], v[q + 4 * S], v[q + 5 * S], v[q + 6 * S], v[q + 7 * S]);
     } else {  // R3 == 16 (S == 1, q == 0)
-      double2 w2 = __ldg(&tab[NS + k]);
-      double2 w4 = __ldg(&tab[2 * NS + k]);
-      double2 w8 = __ldg(&tab[3 * NS + k]);
+      const double2 w2 = W.w[q][LastTw<N>::NW > 1 ? 1 : 0];
+      const double2 w4 = W.w[q][LastTw<N>::NW > 2 ? 2 : 0];
+      const double2 w8 = W.w[q][LastTw<N>::NW > 3 ? 3 : 0];
       twiddle15<DIR>(v, w1, w2, w4, w8);
       dft16<DIR>(v);
     }
@@ -238,7 +255,9 @@ __device__ __forceinline__ void group_sync(int grp) {
 // OPAQUE_TW: hide the twiddle-table pointers from the optimiser for this call.  A kernel that runs several transforms
 // of the same length back to back otherwise gets their (identical) twiddle loads merged and kept live across the
 // transforms in between: up to 48 registers, i.e. spills at 128 registers per thread.
-template <int N, int DIR, bool OPAQUE_TW = false, int NT = 0>
+// EARLY_TW: request the next pass's twiddles before the exchange barrier (hides their latency; measured better in the
+// column kernels, worse in the row kernels, whose register budget is tighter).
+template <int N, int DIR, bool OPAQUE_TW = false, int NT = 0, bool EARLY_TW = true>
 __device__ __forceinline__ void fft_cta(double2 (&v)[16], double2* __restrict__ sm, int t, const Twiddles& tw_in,
                                         int grp = 0) {
   constexpr int T = Cfg<N>::T, R3 = Cfg<N>::R3;
@@ -252,19 +271,33 @@ __device__ __forceinline__ void fft_cta(double2 (&v)[16], double2* __restrict__ 
   group_sync<T, NT>(grp);  // buffer free (previous readers done)
 #pragma unroll
   for (int r = 0; r < 16; ++r) sm[pad_idx(16 * t + r)] = v[sl16(r)];
-  group_sync<T, NT>(grp);
-#pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
   if (Cfg<N>::TWO_PASS) {  // N = 64, 128: last pass radix N/16 over the 16-point sub-transforms
-    last_pass<N, DIR, 16>(v, t, tw.tw2);
+    LastTw<N> W;
+    if (EARLY_TW) last_pass_load<N, 16>(W, t, tw.tw2);   // in flight across the barrier
+    group_sync<T, NT>(grp);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
+    if (!EARLY_TW) last_pass_load<N, 16>(W, t, tw.tw2);
+    last_pass<N, DIR>(v, W);
     return;
   }
   // ---- pass 2: radix 16, Ns = 16 ----
   const int k2 = t & 15;
   {
-    // w_256^(r*k2), r = 1..15, from 4 table entries (r = 1,2,4,8) and at most 3 chained products
-    const double2 w1 = __ldg(&tw.tw2[k2]), w2 = __ldg(&tw.tw2[16 + k2]);
-    const double2 w4 = __ldg(&tw.tw2[32 + k2]), w8 = __ldg(&tw.tw2[48 + k2]);
+    // w_256^(r*k2), r = 1..15, from 4 table entries (r = 1,2,4,8) and at most 3 chained products; requested before the
+    // barrier (the data is in shared memory: no register pressure) so that their latency hides behind the exchange
+    double2 w1, w2, w4, w8;
+    if (EARLY_TW) {
+      w1 = __ldg(&tw.tw2[k2]), w2 = __ldg(&tw.tw2[16 + k2]);
+      w4 = __ldg(&tw.tw2[32 + k2]), w8 = __ldg(&tw.tw2[48 + k2]);
+    }
+    group_sync<T, NT>(grp);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
+    if (!EARLY_TW) {
+      w1 = __ldg(&tw.tw2[k2]), w2 = __ldg(&tw.tw2[16 + k2]);
+      w4 = __ldg(&tw.tw2[32 + k2]), w8 = __ldg(&tw.tw2[48 + k2]);
+    }
     twiddle15<DIR>(v, w1, w2, w4, w8);
   }
   dft16<DIR>(v);
@@ -275,11 +308,14 @@ __device__ __forceinline__ void fft_cta(double2 (&v)[16], double2* __restrict__ 
 #pragma unroll
     for (int r = 0; r < 16; ++r) sm[pad_idx(base + 16 * r)] = v[sl16(r)];
   }
+  // ---- pass 3: radix R3, Ns = 256 ----
+  LastTw<N> W;
+  if (EARLY_TW) last_pass_load<N, 256>(W, t, tw.tw3);
   group_sync<T, NT>(grp);
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
-  // ---- pass 3: radix R3, Ns = 256 ----
-  last_pass<N, DIR, 256>(v, t, tw.tw3);
+  if (!EARLY_TW) last_pass_load<N, 256>(W, t, tw.tw3);
+  last_pass<N, DIR>(v, W);
 }
 #endif  // __CUDACC__
 

@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
     fft::group_sync<T, NT>(grp);
 #pragma unroll
     for (int e = 8; e < 16; ++e) v[e] = sm[pad_idx(t + T * e)];
-    fft::fft_cta<NX, +1, false, NT>(v, sm, t, a.tw, grp);
+    fft::fft_cta<NX, +1, false, NT, D3>(v, sm, t, a.tw, grp);
     if constexpr (D3) {
       if (q == 0) x_product<NX, VMODE, 0, true>(a, v, v, ps, t, t_uv, b, pair);
       else if (q == 1) x_product<NX, VMODE, 1, true>(a, v, v, ps, t, t_uv, b, pair);
@@ -837,7 +837,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_fused_x(XArgs a) {
   }
 
   // ---------------- forward transform of the row pair packed as p_y + i*p_{y+1} ----------------
-  fft::fft_cta<NX, -1, false, NT>(w, sm, t, a.tw, grp);
+  fft::fft_cta<NX, -1, false, NT, D3>(w, sm, t, a.tw, grp);
   fft::group_sync<T, NT>(grp);
 #pragma unroll
   for (int e = 8; e < 16; ++e) sm[pad_idx(t + T * e)] = w[out_slot<NX>(e)];
