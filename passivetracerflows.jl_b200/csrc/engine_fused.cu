@@ -1,6 +1,7 @@
 // Fused 2-D engine, host side: buffers, layouts at the boundary, graph capture, stage sequencing.  The kernels live
 // in fused_kernels.cuh and are instantiated per transform length in fused_inst.cu (one object file per length).
 #include "fused_kernels.cuh"
+#include "expr_flow.h"
 
 namespace ptf {
 
@@ -127,6 +128,40 @@ class FusedEngine final : public Engine {
   void set_velocity_external(int comp, const double* dev, int64_t count) override {
     vs.set_external(comp, dev, count);
     sync_vel();
+  }
+  // PTF_FLOW_EXPR: the expressions are written out as fields u, v once per step (the velocity is frozen at clock.t for
+  // all stages, TAD.jl:718) by a run-time compiled fill kernel; the row kernel reads them like steady arrays
+  void set_velocity_expr(int comp, const char* expr) override {
+    ef.set(comp, expr);
+    bool all = !ef.expr[0].empty() && !ef.expr[1].empty();
+    if (all && ef.stale) {
+      PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+      ef.compile(2);
+    }
+    expr_dirty = true;
+  }
+  void set_flow_time(double t) override {
+    ef.set_time(t, ctx.stream);
+    expr_dirty = true;
+  }
+  void refresh_expr() {
+    if (ctx.d.flow_kind != PTF_FLOW_EXPR || !expr_dirty) return;
+    const size_t nreal = (size_t)nx * ny;
+    bool fresh = false;
+    for (int c = 0; c < 2; ++c)
+      if (exprv[c].n != nreal) {
+        exprv[c].alloc(nreal, &dev_bytes);
+        fresh = true;
+      }
+    if (fresh) {   // one field shared by all members
+      vs.va.arr[0] = exprv[0].p;
+      vs.va.arr[1] = exprv[1].p;
+      vs.va.member_stride = 0;
+      drop_graphs();
+    }
+    ef.fill(ctx.stream, exprv[0].p, exprv[1].p, nullptr, nx, ny, 1, 0, 0, g);
+    ++own_launches;
+    expr_dirty = false;
   }
 
   // ---------------- layout changes at the boundary ----------------
@@ -295,6 +330,7 @@ class FusedEngine final : public Engine {
   }
 
   void step_once(int64_t step_index) override {
+    refresh_expr();
     if (!ab_valid) {  // A,B of the current sol are missing (fresh state): one prologue launch
       run_y(false, true, -1);
       ab_valid = true;
@@ -363,6 +399,7 @@ class FusedEngine final : public Engine {
     DevBuf<double2> backup;
     backup.alloc(nspec);
     PTF_CUDA(cudaMemcpyAsync(backup.p, s0.p, s0.bytes(), cudaMemcpyDeviceToDevice, ctx.stream));
+    refresh_expr();
     if (!ab_valid) {
       run_y(false, true, -1);
       ab_valid = true;
@@ -408,6 +445,9 @@ class FusedEngine final : public Engine {
   size_t work_bytes = 0;
   TwiddleSet twx, twy_own;
   VelocityStore vs;
+  ExprFlow ef;                 // PTF_FLOW_EXPR
+  DevBuf<double> exprv[2];
+  bool expr_dirty = true;
   cufftHandle plan_fwd = 0, plan_inv = 0;
   bool ab_valid = false;
   int tune_ablate_x = 0, tune_ablate_y = 0, tune_stagger_x = 0, tune_stagger_y = 0, n_sm = 148;

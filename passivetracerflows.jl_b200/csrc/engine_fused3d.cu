@@ -6,6 +6,7 @@
 #include <cmath>
 
 #include "fused3d_kernels.cuh"
+#include "expr_flow.h"
 
 #ifdef PTF_WITH_NCCL
 #include <nccl.h>
@@ -174,12 +175,32 @@ class Fused3DEngine final : public Engine {
     vs.set_coeffs(comp, nterms, a);
     sep_dirty = true;
   }
-  // separable flows: the three fields of the step about to run, evaluated at clock.t once (k_sep_fill)
+  void set_velocity_expr(int comp, const char* expr) override {
+    ef.set(comp, expr);
+    bool all = true;
+    for (int a = 0; a < 3; ++a) all = all && !ef.expr[a].empty();
+    if (all && ef.stale) {
+      PTF_CUDA(cudaStreamSynchronize(ctx.stream));
+      ef.compile(3);
+    }
+    sep_dirty = true;
+  }
+  void set_flow_time(double t) override {
+    ef.set_time(t, ctx.stream);
+    sep_dirty = true;
+  }
+  // separable / expression flows: the three fields of the step about to run, evaluated at clock.t once
   void refresh_separable() {
-    if (vs.va.kind != PTF_FLOW_SEPARABLE || !sep_dirty) return;
+    if ((vs.va.kind != PTF_FLOW_SEPARABLE && vs.va.kind != PTF_FLOW_EXPR) || !sep_dirty) return;
     const size_t nreal = (size_t)nx * ny * nzl;
     for (auto& b : sepv)
       if (b.n != nreal) b.alloc(nreal, &dev_bytes);
+    if (vs.va.kind == PTF_FLOW_EXPR) {
+      ef.fill(ctx.stream, sepv[0].p, sepv[1].p, sepv[2].p, nx, ny, nzl, 0, g.zoff, g);
+      ++own_launches;
+      sep_dirty = false;
+      return;
+    }
     k_sep_fill<<<148 * 8, 256, 0, ctx.stream>>>(vs.va, sepv[0].p, sepv[1].p, sepv[2].p, nx, ny, nzl, nz, (int)g.zoff);
     ++own_launches;
     sep_dirty = false;
@@ -441,8 +462,8 @@ class Fused3DEngine final : public Engine {
     // TMEM -> 4 instead of 3 CTAs per SM (measured: 256^3 row kernel 0.252 -> 0.185 ms, 1024^3 19.8 -> 17.2 ms)
     const char* xd = std::getenv("PTF_X_DIRECT");
     int vmode = (xd && std::atoi(xd) == 0) ? 0 : 3;
-    if (vs.va.kind == PTF_FLOW_SEPARABLE) {
-      if (!sepv[0].p) throw Error(PTF_EINVAL, "separable velocity tables have not been set");
+    if (vs.va.kind == PTF_FLOW_SEPARABLE || vs.va.kind == PTF_FLOW_EXPR) {
+      if (!sepv[0].p) throw Error(PTF_EINVAL, "separable tables / velocity expressions have not been set");
       for (int c = 0; c < 3; ++c) a.va.arr[c] = sepv[c].p;
     } else if (!vs.va.arr[0] || !vs.va.arr[1] || !vs.va.arr[2]) {
       throw Error(PTF_EINVAL, "velocity fields have not been set (ptf_set_velocity / callback)");
@@ -764,7 +785,8 @@ class Fused3DEngine final : public Engine {
   DevBuf<double> cE, cE2, cZ, cA, cB, cG;
   TwiddleSet twx, twy_own, twz_own;
   VelocityStore vs;
-  DevBuf<double> sepv[3];   // separable flows: u, v, w of the current step (local planes)
+  DevBuf<double> sepv[3];   // separable / expression flows: u, v, w of the current step (local planes)
+  ExprFlow ef;              // PTF_FLOW_EXPR: run-time compiled expressions (fill kernel)
   bool sep_dirty = true;
   cufftHandle plan_fwd = 0, plan_inv = 0;
   bool ac_valid = false;
@@ -799,7 +821,6 @@ bool fused3d_engine_supports(const Context& ctx, std::string* why) {
   if (!is_fused3_size(g.nx) || !is_fused3_size(g.ny) || !is_fused3_size(g.nz))
     return no("nx, ny and nz must be powers of two in [64, 1024]");
   if (g.B != 1) return no("3-D ensembles run on the cuFFT engine");
-  if (ctx.d.flow_kind == PTF_FLOW_EXPR) return no("expression flows (PTF_FLOW_EXPR) run on the cuFFT pipelines");
   if (ctx.d.flow_kind == PTF_FLOW_LAYERED) return no("layered flows are 2-D per layer");
   const int P = g.slab ? g.P : 1;
   if ((P & (P - 1)) || P > 16) return no("the number of ranks must be a power of two, at most 16");

@@ -57,6 +57,26 @@ extern "C" __global__ void __launch_bounds__(256) ptf_product_expr(double* __res
                          ptf_point(ptf_coord(x0, i + 1, dx), y, z, t, a.y, c.y, d.y));
   }
 }
+// The same expressions written out as fields u, v, w at clock.t (fused engines: the velocity is frozen for all stages of
+// a step, so it is evaluated once per step and the row kernels read it like steady arrays).
+extern "C" __global__ void __launch_bounds__(256) ptf_fill_expr(double* __restrict__ uo, double* __restrict__ vo,
+    double* __restrict__ wo, const double* __restrict__ tptr, long long nx, long long ny, long long nzl,
+    long long joff, long long koff, double x0, double dx, double y0, double dy, double z0, double dz) {
+  const double t = *tptr;
+  const long long npts = nx * ny * nzl;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += (long long)gridDim.x * blockDim.x) {
+    const long long i = p % nx, j = (p / nx) % ny, k = p / (nx * ny);
+    const double x = ptf_coord(x0, i, dx), y = ptf_coord(y0, joff + j, dy), z = ptf_coord(z0, koff + k, dz);
+    uo[p] = (PTF_EXPR_U);
+#if PTF_ND >= 2
+    vo[p] = (PTF_EXPR_V);
+#endif
+#if PTF_ND >= 3
+    wo[p] = (PTF_EXPR_W);
+#endif
+    (void)x; (void)y; (void)z; (void)t;
+  }
+}
 )SRC";
 }  // namespace
 
@@ -112,6 +132,7 @@ void ExprFlow::compile(int ndim) {
   }
   PTF_CUDA(cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   PTF_CUDA(cudaLibraryGetKernel(&kern, lib, "ptf_product_expr"));
+  PTF_CUDA(cudaLibraryGetKernel(&kern_fill, lib, "ptf_fill_expr"));
   if (!d_t.p) {
     d_t.alloc(1);
     PTF_CUDA(cudaMemset(d_t.p, 0, sizeof(double)));
@@ -138,6 +159,18 @@ void ExprFlow::launch(cudaStream_t st, int blocks, int nbatch, double* g0, const
   const double* tptr = d_t.p;
   void* args[] = {&g0, &g1, &g2, &tptr, &a_nx, &a_ny, &a_nzl, &a_joff, &a_koff, &x0, &dx, &y0, &dy, &z0, &dz};
   PTF_CUDA(cudaLaunchKernel((const void*)kern, dim3((unsigned)blocks, (unsigned)nbatch, 1), dim3(256, 1, 1), args, 0, st));
+}
+
+void ExprFlow::fill(cudaStream_t st, double* u, double* v, double* w, int64_t nx, int64_t ny, int64_t nzl, int64_t joff,
+                    int64_t koff, const Geometry& g) {
+  if (stale || !kern_fill || compiled_ndim != g.ndim) throw Error(PTF_EINVAL, "velocity expressions are not compiled");
+  long long a_nx = nx, a_ny = ny, a_nzl = nzl, a_joff = joff, a_koff = koff;
+  double x0 = -g.Lx / 2, dx = g.Lx / (double)g.nx;
+  double y0 = g.ndim >= 2 ? -g.Ly / 2 : 0.0, dy = g.ndim >= 2 ? g.Ly / (double)g.ny : 0.0;
+  double z0 = g.ndim >= 3 ? -g.Lz / 2 : 0.0, dz = g.ndim >= 3 ? g.Lz / (double)g.nz : 0.0;
+  const double* tptr = d_t.p;
+  void* args[] = {&u, &v, &w, &tptr, &a_nx, &a_ny, &a_nzl, &a_joff, &a_koff, &x0, &dx, &y0, &dy, &z0, &dz};
+  PTF_CUDA(cudaLaunchKernel((const void*)kern_fill, dim3(148 * 16, 1, 1), dim3(256, 1, 1), args, 0, st));
 }
 
 }  // namespace ptf

@@ -425,9 +425,9 @@ int32_t ptf_create(const ptf_desc* d, ptf_handle** out) {
     int want = d->engine;
     const bool one_d = h->ctx.g.ndim == 1;
     const bool expr_flow = d->flow_kind == PTF_FLOW_EXPR;
-    if (expr_flow && want == PTF_ENGINE_FUSED)
-      throw Error(PTF_EUNSUPPORTED, "fused engine: expression flows (PTF_FLOW_EXPR) run on the cuFFT pipelines");
-    if (expr_flow && want == PTF_ENGINE_AUTO) want = PTF_ENGINE_CUFFT;
+    if (expr_flow && one_d && want == PTF_ENGINE_FUSED)
+      throw Error(PTF_EUNSUPPORTED, "fused 1-D engine: expression flows (PTF_FLOW_EXPR) run on the cuFFT pipeline");
+    if (expr_flow && one_d && want == PTF_ENGINE_AUTO) want = PTF_ENGINE_CUFFT;
     if (h->ctx.g.slab2d) {
       if (want == PTF_ENGINE_FUSED) throw Error(PTF_EUNSUPPORTED, "fused engine: 2-D slab decomposition runs on the cuFFT pipeline");
       h->engine = make_slab2d_engine(h->ctx);

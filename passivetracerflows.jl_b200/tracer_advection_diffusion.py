@@ -98,7 +98,8 @@ class ExpressionFlow:
     ``x, y, z, t`` (device math: ``sin``, ``cos``, ``exp``, …, ``pi``), e.g. ``u="(sin(z) + cos(y)) * (1 + 0.5*sin(t))"``.
     They play the role of the reference's ``u(x, y, z, t)`` closures (TAD.jl:268-348): evaluated at ``clock.t`` on the
     grid points, but in registers inside the product kernel (compiled at run time with NVRTC) — zero HBM bytes and no
-    per-step upload.  Runs on the cuFFT pipelines (any size, 1-D/2-D/3-D, slab-decomposed)."""
+    per-step upload.  Runs on every engine: in the cuFFT pipelines (any size, 1-D/2-D/3-D, slab-decomposed) inside the product
+    kernel, on the fused 2-D / 3-D engines through a fill kernel that writes the fields once per step."""
     u: str = "0.0"
     v: Optional[str] = None
     w: Optional[str] = None
