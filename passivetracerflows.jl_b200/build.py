@@ -29,7 +29,18 @@ def needs_build():
         return True
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "ptf_b200.h"),
                                                                  os.path.abspath(__file__)]
-    return _newest(deps) > os.path.getmtime(LIB)
+    newest = _newest(deps)
+    if newest > os.path.getmtime(LIB):
+        return True
+    # every object must also be newer than its own source and every header (a file edited WHILE a build was running
+    # leaves a fresh-looking library linked from a stale object)
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    jobs = [(s, s.replace(".cu", ".o")) for s in SOURCES] + [("fused_inst.cu", f"fused_inst_{n}.o") for n in FUSED_SIZES]
+    for src, o in jobs:
+        po = os.path.join(HERE, "build", o)
+        if not os.path.exists(po) or os.path.getmtime(po) < _newest(hdrs + [os.path.join(CSRC, src)]):
+            return True
+    return False
 
 
 def build(force=False, verbose=False, with_nccl=True, variant=None, defines=()):
