@@ -235,3 +235,27 @@ def test_fused3d_flattened_strides_match_the_block_layouts(P, ny, nz):
         want_out = (((r * nkx + kr) * (nzl // 8) + zl // 8) * nyl + ll) * 8 + zl % 8
         got_out = ((kr * (nzl // 8) + zl // 8) * nyl + t) * 8 + zl % 8 + e * out_se + (e >> esh) * out_sr
         assert want_out == got_out
+
+
+@pytest.mark.parametrize("P", [1, 2, 8])
+def test_fused3d_z_column_offsets_match_the_block_layouts(P):
+    """fused_kernels.cuh, k_fused_y<..., D3>: element z of column cid = kr*nyl + ll is gathered from block r = z >> zsh at
+    pin + (zl >> 3)*nyl*8 + (zl & 7) and its A / C value stored into block p = z >> zsh at (cid << zsh) + zl."""
+    nkx, ny, nz = 5, 64, 128
+    nyl, nzl = ny // P, nz // P
+    zsh = nzl.bit_length() - 1
+    blk = nkx * nyl * nzl
+    rng = np.random.default_rng(P)
+    for _ in range(50):
+        kr, ll, z = int(rng.integers(nkx)), int(rng.integers(nyl)), int(rng.integers(nz))
+        cid = kr * nyl + ll
+        r, zl = z >> zsh, z & (nzl - 1)
+        assert (r, zl) == (z // nzl, z % nzl)
+        # gather: Psrc[r] = base + r*blk ; [r][kr][zl/8][ll][zl%8]
+        got = r * blk + (kr * (nzl >> 3) * nyl + ll) * 8 + (zl >> 3) * nyl * 8 + (zl & 7)
+        want = (((r * nkx + kr) * (nzl // 8) + zl // 8) * nyl + ll) * 8 + zl % 8
+        assert got == want
+        # store: Adst[p] = base + p*blk ; [p][kr][ll][zl]
+        got = r * blk + (cid << zsh) + zl
+        want = ((r * nkx + kr) * nyl + ll) * nzl + zl
+        assert got == want
