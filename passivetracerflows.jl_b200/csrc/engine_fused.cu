@@ -75,7 +75,9 @@ class FusedEngine final : public Engine {
       tune_stagger_y = env_int("PTF_STAGGER_Y", 25000);
       PTF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx.device));
       tune_ablate_y = env_int("PTF_ABLATE_Y", 0);
-      tune_x_direct = env_int("PTF_X_DIRECT", 1);   // measured: row kernel 0.229 -> 0.210 ms at 4096^2 (profiles/r02_*)
+      // 1: velocities loaded after the transforms (row kernel 0.229 -> 0.206 ms at 4096^2); 2 (default): row 0's product
+      // parked in TMEM too, no shared-memory parking row, no spills (0.206 -> 0.192 ms; profiles/r02_vmode4.txt)
+      tune_x_direct = env_int("PTF_X_DIRECT", 2);
     }
     PTF_DISPATCH_N(ny, fused_prep);
     if (nx != ny) PTF_DISPATCH_N(nx, fused_prep);
@@ -292,7 +294,7 @@ class FusedEngine final : public Engine {
       a.stagger = ctas >= 4L * a.first_wave ? tune_stagger_x : 0;
     }
     int vmode = (vs.va.kind == PTF_FLOW_SEPARABLE) ? 2 : (vs.va.ushift ? 1 : 0);
-    if (vmode != 2 && tune_x_direct) vmode = 3;
+    if (vmode != 2 && tune_x_direct) vmode = tune_x_direct == 2 ? 4 : 3;
     if (vmode != 2 && (!vs.va.arr[0] || !vs.va.arr[1]))
       throw Error(PTF_EINVAL, "velocity fields have not been set (ptf_set_velocity / callback)");
     PTF_DISPATCH_N(nx, fused_launch_x, vmode, &a, nb, ctx.stream, n_sm);

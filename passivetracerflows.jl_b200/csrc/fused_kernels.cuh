@@ -550,7 +550,7 @@ template <int NX, int VMODE, bool D3W = false, bool D3 = false>
 __device__ __forceinline__ void x_request_uv(const XArgs& a, size_t voff, int q, int t, uint32_t t_uv) {
   constexpr int T = Cfg<NX>::T;
   constexpr int UB = 8;  // velocity request batch
-  if (VMODE == 3) {
+  if (VMODE >= 3) {
     // direct mode: only pull the rows into L2 now (one request per 32-byte sector); x_product loads them from there
     // after the transform — no TMEM parking, and this warp does not wait here for HBM
     if ((t & 3) == 0) {
@@ -593,20 +593,22 @@ __device__ __forceinline__ void x_product(const XArgs& a, const double2 (&v)[16]
                                           double* __restrict__ ps, int t, uint32_t t_uv, int b, int pair) {
   constexpr int T = Cfg<NX>::T;
   const int row = 2 * pair + Q;
-  constexpr int PB = VMODE == 3 ? 8 : 4;  // velocity fetch batch
-  const size_t vi0 = VMODE == 3 ? fft::opaque((D3 ? (size_t)b * a.ny * NX : (size_t)b * a.va.member_stride) +
+  constexpr int PB = VMODE >= 3 ? 8 : 4;  // velocity fetch batch
+  const size_t vi0 = VMODE >= 3 ? fft::opaque((D3 ? (size_t)b * a.ny * NX : (size_t)b * a.va.member_stride) +
                                               (size_t)row * NX + t)
                                 : 0;
 #pragma unroll
   for (int c = 0; c < 16 / PB; ++c) {
     double2 uv[PB];
-    if (VMODE == 3) {
+    if (VMODE >= 3) {
 #pragma unroll
       for (int j = 0; j < PB; ++j)
         uv[j] = make_double2(tmem::ldg64(a.va.arr[0] + vi0 + T * (PB * c + j)),
                              tmem::ldg64(a.va.arr[1] + vi0 + T * (PB * c + j)));
     } else if (VMODE != 2) tmem::ldn<PB>(t_uv + 4 * PB * c, uv);
     double pprev = 0.0;
+    double2 p0[PB / 2];   // VMODE 4 (2-D, row 1): row 0's parked products of this batch, two points per entry
+    if (!D3 && VMODE == 4 && Q == 1) tmem::ldn<PB / 2>(t_uv + 2 * PB * c, p0);
 #pragma unroll
     for (int j = 0; j < PB; ++j) {
       const int e = PB * c + j, x = t + T * e;
@@ -625,11 +627,15 @@ __device__ __forceinline__ void x_product(const XArgs& a, const double2 (&v)[16]
         if (j & 1) tmem::st1(t_uv + 32 * Q + 2 * (e - 1), make_double2(pprev, p));   // points per 4-column entry
         pprev = p;
       } else if (D3) ps[Q * NX + x] = p;
+      else if (VMODE == 4 && Q == 0) {           // 2-D direct mode 4: row 0's product parked in TMEM as well
+        if (j & 1) tmem::st1(t_uv + 2 * (e - 1), make_double2(pprev, p));
+        pprev = p;
+      } else if (VMODE == 4) w[e] = make_double2((j & 1) ? p0[j / 2].y : p0[j / 2].x, p);
       else if (Q == 0) ps[x] = p;                // row 0: parked in shared memory while row 1 runs
       else w[e] = make_double2(ps[x], p);        // row 1: packed with row 0 as p_y + i*p_{y+1} for the forward FFT
     }
   }
-  if (D3 && VMODE == 3) tmem::wait_st();
+  if ((D3 && VMODE == 3) || (!D3 && VMODE == 4 && Q == 0)) tmem::wait_st();
 }
 // 3-D: v = gz(row 0) + i*gz(row 1);  p_q -= w_q * gz_q  (TAD.jl:781), completed in the shared-memory parking rows
 template <int NX, int VMODE>
@@ -688,7 +694,9 @@ __device__ __forceinline__ void x_product_z(const XArgs& a, const double2 (&v)[1
   if (VMODE == 3) tmem::wait_st();
 }
 
-// VMODE 0: velocity arrays; 1: arrays + layered shift U(y,b); 2: separable tables (zero HBM bytes)
+// VMODE 0: velocity arrays; 1: arrays + layered shift U(y,b); 2: separable tables (zero HBM bytes);
+// 3: arrays, direct (rows prefetched to L2 before the inverse transform, loaded after it; 3-D default);
+// 4: 3 + row 0's product parked in TMEM instead of shared memory (2-D default; launched without the parking row)
 //
 // Memory choreography (what the ablation study in profiles/ asked for): A[k][y], A[k][y+1] are 32 contiguous bytes,
 // so ONE 256-bit load per k fetches both rows of the pair (half the L1 tag look-ups of two 16-byte gathers, one
@@ -1027,6 +1035,7 @@ void prep_x_nt() {
     allow_smem(k_fused_x<NX, 0, NT>, x_smem<NX, NT>() + g_smem_pad);
     allow_smem(k_fused_x<NX, 2, NT>, x_smem<NX, NT>() + g_smem_pad);
     allow_smem(k_fused_x<NX, 3, NT>, x_smem<NX, NT>() + g_smem_pad);
+    allow_smem(k_fused_x<NX, 4, NT>, y_smem<NX, NT>() + g_smem_pad);
   }
 }
 template <int NX>
@@ -1071,6 +1080,7 @@ void launch_x_nt(int vmode, const XArgs& a, int nb, cudaStream_t st) {
     size_t sm = x_smem<NX, NT>() + g_smem_pad;
     if (vmode == 2) k_fused_x<NX, 2, NT><<<grid, NT, sm, st>>>(a);
     else if (vmode == 3) k_fused_x<NX, 3, NT><<<grid, NT, sm, st>>>(a);
+    else if (vmode == 4) k_fused_x<NX, 4, NT><<<grid, NT, y_smem<NX, NT>() + g_smem_pad, st>>>(a);
     else k_fused_x<NX, 0, NT><<<grid, NT, sm, st>>>(a);
   }
 }

@@ -11,7 +11,7 @@ dt = 0.5 * 2.785 / (0.1 * 2 * (nx / 2) ** 2)
 flow = P.TwoDAdvectingFlow(u=lambda x, y: 0.2 * np.cos(x) * np.sin(y), v=lambda x, y: -0.2 * np.sin(x) * np.cos(y))
 x = -np.pi + (2 * np.pi / nx) * np.arange(nx)
 c0 = 0.5 * np.exp(-((x[None, :] - 0.4 * np.pi) ** 2 + x[:, None] ** 2) / (2 * 0.15 ** 2))
-KEYS = ["PTF_PF_STATE", "PTF_PF_VEL", "PTF_PF_AHEAD_Y", "PTF_PF_AHEAD_X", "PTF_SMEM_PAD", "PTF_ABLATE_X", "PTF_ABLATE_Y", "PTF_STAGGER_X", "PTF_STAGGER_Y", "PTF_NT"]
+KEYS = ["PTF_PF_STATE", "PTF_PF_VEL", "PTF_PF_AHEAD_Y", "PTF_PF_AHEAD_X", "PTF_SMEM_PAD", "PTF_ABLATE_X", "PTF_ABLATE_Y", "PTF_STAGGER_X", "PTF_STAGGER_Y", "PTF_NT", "PTF_X_DIRECT"]
 for spec in (sys.argv[1:] or [""]):
     for k in KEYS:
         os.environ.pop(k, None)
